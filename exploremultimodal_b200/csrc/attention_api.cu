@@ -1,0 +1,52 @@
+// C-ABI entry points of K1 (see include/mome.h): argument checks and dispatch between the fp32
+// CUDA-core kernels (attention_simt.cu) and the bf16 tensor-core kernels (attention_mma.cu).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace mome {
+int attn_fwd_simt_dispatch(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse,
+                           int num_seqs, int max_seq_len, int H, float scale, cudaStream_t stream);
+int attn_bwd_simt_dispatch(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
+                           const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len,
+                           int H, float scale, cudaStream_t stream);
+int attn_fwd_mma(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse, int num_seqs,
+                 int max_seq_len, int H, float scale, cudaStream_t stream);
+int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask,
+                 const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len, int H, float scale,
+                 cudaStream_t stream);
+
+// MOME_ATTN_SIMT=1 forces the CUDA-core kernels for bf16 too (cross-check in tests / debugging).
+static bool force_simt() {
+  static const bool v = [] {
+    const char* e = getenv("MOME_ATTN_SIMT");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+}  // namespace mome
+
+using namespace mome;
+
+extern "C" int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse,
+                             int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, void* stream) {
+  MOME_REQUIRE(dtype == MOME_F32 || dtype == MOME_BF16, "attn_fwd: unknown dtype %d", dtype);
+  MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_fwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
+  if (num_seqs == 0 || tokens == 0) return MOME_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MOME_BF16 && !force_simt())
+    return attn_fwd_mma(qkv, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, s);
+  return attn_fwd_simt_dispatch(qkv, dtype, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, s);
+}
+
+extern "C" int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
+                             const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens, int32_t num_seqs,
+                             int32_t max_seq_len, int32_t num_heads, float scale, void* stream) {
+  MOME_REQUIRE(dtype == MOME_F32 || dtype == MOME_BF16, "attn_bwd: unknown dtype %d", dtype);
+  MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_bwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
+  if (num_seqs == 0 || tokens == 0) return MOME_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MOME_BF16 && !force_simt())
+    return attn_bwd_mma(qkv, out, dout, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, num_heads, scale, s);
+  return attn_bwd_simt_dispatch(qkv, out, dout, dtype, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, num_heads, scale, s);
+}

@@ -1,0 +1,44 @@
+// Shared host-side plumbing of libmome: error reporting, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/mome.h"
+
+namespace mome {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return MOME_ERR_CUDA;
+  }
+  return MOME_OK;
+}
+
+#define MOME_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      mome::set_error(__VA_ARGS__);  \
+      return MOME_ERR_ARG;           \
+    }                                \
+  } while (0)
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace mome

@@ -1,0 +1,211 @@
+"""Objectives that call the MoME backbone: MLM, ITC, ITM, VQA (reference models/vlmo/objectives.py:
+compute_mlm :40, compute_itc :81, compute_itm :239, compute_vqa :317, GatherLayer :392).
+
+ITC is the hot-path piece: the gather of L2-normalised features across ranks, both similarity
+products, both cross-entropies and the accuracies run in libmome's fused K4 kernels; the [bs, W*bs]
+logit matrices are never materialised (only the local [bs, bs] blocks ITM needs are returned).
+MLM / ITM / VQA are callers of the backbone kept in stock PyTorch like the reference, but written
+without the reference's per-step host synchronisations (boolean-mask indexing, `.item()` loops).
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _lib as L
+
+
+def compute_accuracy(logits, target):
+    """Reference objectives.py:24-37, without the boolean-index host sync: returns 0-dim tensors."""
+    valid = target != -100
+    hit = (logits.argmax(dim=-1) == target) & valid
+    count = valid.sum()
+    return hit.sum().float() / count.clamp(min=1).float(), count
+
+
+# --------------------------------------------------------------------------------------------- MLM
+def compute_mlm(model, batch):
+    """Reference objectives.py:40-78. Masked rows are compacted with a stable sort instead of
+    boolean indexing (no host sync): the first K rows hold every masked position (K = capacity,
+    `config.train.mlm_capacity`, default 25 % of the text tokens, all of them for small batches);
+    the padding rows carry label -100 and are ignored by the cross-entropy exactly like the
+    reference's `ignore_index`."""
+    has_img = any('image' in k for k in batch.keys() if batch[k] is not None)
+    infer = model.infer(batch, infer_mode='img-txt' if has_img else 'txt_only', mask_txt=True, mask_img=False)
+    txt_feats, labels = infer['txt_feats'], infer['txt_labels']
+    B, T, d = txt_feats.shape
+    flat = labels.reshape(-1)
+    cap = getattr(model.config.train, 'mlm_capacity', 0.25)
+    K = B * T if B * T <= 256 else min(B * T, max(256, int(cap * B * T)))
+    order = torch.argsort((flat == -100).to(torch.int8), stable=True)[:K]
+    rows = txt_feats.reshape(B * T, d)[order]
+    tgt = flat[order]
+    with model.transformer._autocast():
+        logits = model.mlm_head(rows)
+    acc, count = compute_accuracy(logits, tgt)
+    loss = F.cross_entropy(logits.float().view(-1, model.config.model.vocab_size), tgt.view(-1), ignore_index=-100,
+                           reduction='sum') / count.clamp(min=1).float()
+    return {'mlm_task_loss': loss, 'mlm_logits': logits, 'mlm_labels': tgt, 'mlm_ids': infer['txt_ids'],
+            'mlm_mean_acc': acc, 'mlm_count': count}
+
+
+# --------------------------------------------------------------------------------------------- ITC
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+class _ItcFn(torch.autograd.Function):
+    """loss = (CE(i2t) + CE(t2i)) / 2 over this rank's rows against every rank's columns.
+
+    forward: all_gather of the two [bs, dim] feature blocks (NCCL) -> mome_itc_fwd.
+    backward: mome_itc_bwd -> reduce_scatter of the column terms (the reference all_reduces the full
+    [W*bs, dim] gradient and slices, objectives.py:416-426) + local-row terms; d_temp.
+    """
+
+    @staticmethod
+    def forward(ctx, i_feat, t_feat, temp, global_reduce):
+        i_feat, t_feat = i_feat.contiguous().float(), t_feat.contiguous().float()
+        temp = temp.detach().reshape(1).float().contiguous()
+        bs, dim = i_feat.shape
+        world, rank = _world() if global_reduce else (1, 0)
+        if world > 1:
+            all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=i_feat.device)
+            all_t = torch.empty_like(all_i)
+            dist.all_gather_into_tensor(all_i, i_feat)
+            dist.all_gather_into_tensor(all_t, t_feat)
+        else:
+            all_i, all_t = i_feat, t_feat
+        dev = i_feat.device
+        loss_sum = torch.empty(2, dtype=torch.float32, device=dev)
+        correct = torch.empty(2, dtype=torch.int32, device=dev)
+        lse = torch.empty(2 * bs, dtype=torch.float32, device=dev)
+        sim_local = torch.empty(2, bs, bs, dtype=torch.float32, device=dev)
+        L.check(L.lib().mome_itc_fwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
+                                     temp.data_ptr(), bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
+                                     lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd')
+        ctx.save_for_backward(i_feat, t_feat, all_i, all_t, temp, lse)
+        ctx.dims = (bs, dim, world, rank)
+        per_dir = loss_sum / bs
+        loss = per_dir.sum() * 0.5
+        ctx.mark_non_differentiable(per_dir, correct, sim_local)
+        return loss, per_dir, correct, sim_local
+
+    @staticmethod
+    def backward(ctx, dloss, _a, _b, _c):
+        i_feat, t_feat, all_i, all_t, temp, lse = ctx.saved_tensors
+        bs, dim, world, rank = ctx.dims
+        dev = i_feat.device
+        g = dloss.reshape(1).float().contiguous()
+        d_i, d_t = torch.empty_like(i_feat), torch.empty_like(t_feat)
+        d_all_i, d_all_t = torch.empty_like(all_i), torch.empty_like(all_t)
+        d_temp = torch.zeros(1, dtype=torch.float32, device=dev)
+        L.check(L.lib().mome_itc_bwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
+                                     temp.data_ptr(), bs, world, rank, dim, lse.data_ptr(), g.data_ptr(),
+                                     d_i.data_ptr(), d_t.data_ptr(), d_all_i.data_ptr(), d_all_t.data_ptr(),
+                                     d_temp.data_ptr(), L.stream()), 'mome_itc_bwd')
+        if world > 1:
+            own_i, own_t = torch.empty_like(i_feat), torch.empty_like(t_feat)
+            dist.reduce_scatter_tensor(own_i, d_all_i)
+            dist.reduce_scatter_tensor(own_t, d_all_t)
+            d_i += own_i
+            d_t += own_t
+        else:
+            d_i += d_all_i
+            d_t += d_all_t
+        return d_i, d_t, d_temp.reshape(()), None
+
+
+def itc_loss_from_feats(i_feat, t_feat, temp, global_reduce):
+    """Fused ITC on already L2-normalised features. Returns the reference's dict entries
+    (objectives.py:182-193); `sim_i2t` / `sim_t2i` are the local [bs, bs] blocks (what ITM reads,
+    objectives.py:251-255), not the full [bs, W*bs] matrices, which are never formed."""
+    bs = i_feat.shape[0]
+    loss, per_dir, correct, sim_local = _ItcFn.apply(i_feat, t_feat, temp, bool(global_reduce))
+    count = torch.full((), bs, dtype=torch.int64, device=i_feat.device)
+    return {'itc_task_loss': loss, 'i2t_Loss': per_dir[0], 't2i_Loss': per_dir[1],
+            'sim_i2t': sim_local[0], 'sim_t2i': sim_local[1],
+            'itc_i2t_mean_acc': correct[0].float() / bs, 'itc_i2t_count': count,
+            'itc_t2i_mean_acc': correct[1].float() / bs, 'itc_t2i_count': count}
+
+
+def compute_itc(model, batch):
+    """Reference objectives.py:81-193, global-reduce (:99-108) and naive (:166-171) branches."""
+    with torch.no_grad():
+        model.itc_temp.data.clamp_(0, 4.6052)
+    temp = model.itc_temp.exp()
+    img_infer = model.infer(batch, infer_mode='img_only')
+    txt_infer = model.infer(batch, infer_mode='txt_only')
+    with model.transformer._autocast():
+        i_feat = model.itc_head(img_infer['co_feats'][:, 0], 'v')
+        t_feat = model.itc_head(txt_infer['co_feats'][:, 0], 'l')
+    ret = itc_loss_from_feats(i_feat, t_feat, temp, model.config.train.global_reduce)
+    ret['itc_temp'] = temp.detach()
+    return ret
+
+
+# --------------------------------------------------------------------------------------------- ITM
+def pick_negatives_multinomial(weights):
+    """One batched on-device draw per row: same distribution as the reference's
+    `torch.multinomial(w[b], 1).item()` loop (objectives.py:268-277) without its 2*bs host syncs."""
+    return torch.multinomial(weights, 1).squeeze(1)
+
+
+def pick_negatives_argmax(weights):
+    """Deterministic chooser for parity runs (hardest negative)."""
+    return weights.argmax(dim=1)
+
+
+def compute_itm(model, batch, sim_dict=None):
+    """Reference objectives.py:239-314."""
+    txt_ids, txt_mask, img = batch['text_ids'], batch['text_mask'], batch['image']
+    bs = img.size(0)
+    output_pos = model.infer(batch, infer_mode='img-txt')
+    with torch.no_grad():
+        if sim_dict is not None:
+            w_i2t = F.softmax(sim_dict['sim_i2t'][:, :bs].float(), dim=1) + 1e-5
+            w_t2i = F.softmax(sim_dict['sim_t2i'][:, :bs].float(), dim=1) + 1e-5
+        else:
+            w_i2t = F.softmax(torch.randn(bs, bs, device=img.device), dim=1) + 1e-5
+            w_t2i = F.softmax(torch.randn(bs, bs, device=img.device), dim=1) + 1e-5
+        w_i2t.fill_diagonal_(0)
+        w_t2i.fill_diagonal_(0)
+        pick = getattr(model, 'itm_negative_picker', pick_negatives_multinomial)
+        neg_img, neg_txt = pick(w_t2i), pick(w_i2t)
+    neg_batch = {
+        'text_ids': torch.cat([txt_ids, txt_ids[neg_txt]], dim=0),
+        'text_mask': torch.cat([txt_mask, txt_mask[neg_txt]], dim=0),
+        'image': torch.cat([img[neg_img], img], dim=0),
+    }
+    output_neg = model.infer(neg_batch, infer_mode='img-txt')
+    cls_feat = torch.cat([output_pos['cls_feats'], output_neg['cls_feats']], dim=0)
+    with model.transformer._autocast():
+        itm_logits = model.itm_head(cls_feat)
+    itm_labels = torch.cat([torch.ones(bs, dtype=torch.long, device=img.device),
+                            torch.zeros(2 * bs, dtype=torch.long, device=img.device)], dim=0)
+    itm_loss = F.cross_entropy(itm_logits.float(), itm_labels)
+    acc, count = compute_accuracy(itm_logits, itm_labels)
+    return {'itm_task_loss': itm_loss, 'itm_logits': itm_logits, 'itm_labels': itm_labels, 'itm_mean_acc': acc,
+            'itm_count': count, 'itm_neg_img': neg_img, 'itm_neg_txt': neg_txt}
+
+
+# --------------------------------------------------------------------------------------------- VQA
+def compute_vqa_score(logits, target):
+    """Reference objectives.py:12-21."""
+    pred = logits.argmax(dim=1, keepdim=True)
+    return target.gather(1, pred).sum() / logits.shape[0], logits.shape[0]
+
+
+def compute_vqa(model, batch):
+    """Reference objectives.py:317-389 (ISDA and R-Drop branches are off in every BASELINE config
+    and not carried over)."""
+    infer = model.infer(batch, infer_mode='img-txt', mask_txt=False, mask_img=False)
+    with model.transformer._autocast():
+        vqa_logits = model.vqa_classifier(infer['cls_feats'])
+    ret = {'vqa_logits': vqa_logits, 'vqa_count': vqa_logits.size(0)}
+    vqa_targets = batch['vqa_targets']
+    if vqa_targets is not None:
+        loss = F.binary_cross_entropy_with_logits(vqa_logits.float(), vqa_targets) * vqa_targets.shape[1]
+        score, count = compute_vqa_score(vqa_logits, vqa_targets)
+        ret.update({'vqa_task_loss': loss, 'vqa_targets': vqa_targets, 'vqa_mean_score': score, 'vqa_count': count})
+    return ret

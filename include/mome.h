@@ -1,0 +1,150 @@
+/* libmome — C ABI of the B200-native VLMo MoME hot path.
+ *
+ * The reference (fanzhongyi/ExploreMultiModal) is pure Python: its "FFI" for this path is the set of
+ * ATen / cuBLAS / NCCL calls its nn.Modules make. Each entry point below replaces one of those call
+ * groups; the citation names the reference lines (relative to the reference root) it stands in for.
+ * Host code (exploremultimodal_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain pointers (device memory unless noted), explicit sizes, the CUDA stream as an
+ * opaque pointer (cudaStream_t). No allocation, no host synchronisation, no implicit stream.
+ * Return 0 on success, otherwise a MomeStatus; mome_last_error() gives the text (thread local).
+ * dtype codes: 0 = fp32, 1 = bf16. fp32 runs on CUDA cores (validation mode, 1e-4 parity);
+ * bf16 runs the tcgen05/TMEM/TMA kernels.
+ */
+#ifndef MOME_H_
+#define MOME_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOME_ABI_VERSION 1
+#define MOME_MAX_GROUPS 4
+
+enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
+enum MomeDtype { MOME_F32 = 0, MOME_BF16 = 1 };
+
+int mome_version(void);
+const char* mome_last_error(void);
+/* number of SMs of the current device (grid sizing; 148 on B200) */
+int mome_sm_count(void);
+
+/* ---- K3: LayerNorm and the HBM-bound epilogues -------------------------------------------------
+ * reference: vlmo.py:26-36 (LayerNorm factory), vlmo.py:188,192,196 (norm1/norm2), vlmo.py:355,376,
+ * 386,413 (final norm); eps 1e-12 from vlmo_module.py:21-23. */
+int mome_ln_fwd(const float* x, const float* weight, const float* bias, void* y, int y_dtype, float* mean,
+                float* rstd, int64_t rows, int64_t d, float eps, void* stream);
+/* dx_out = (dres ? dres : 0) + LN'(dy); dweight/dbias are ACCUMULATED (+=) in fp32. */
+int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
+                const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
+                int64_t rows, int64_t d, void* stream);
+/* LayerScale backward (reference vlmo.py:194-196, `x + gamma * branch`):
+ *   dbranch = gamma * dx (cast to dbranch_dtype); dgamma += sum_rows dx * branch;
+ *   dbias += sum_rows dbranch (bias of the Linear that produced `branch`). gamma may be NULL (=1). */
+int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
+                   int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* stream);
+/* out[j] += sum_rows x[r, j]  (bias gradients of qkv / fc1) */
+int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+/* fp32 -> bf16 cast (weights, once per optimizer step) */
+int mome_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- K2: grouped GEMM with fused epilogues --------------------------------------------------------
+ * reference: F.linear at vlmo.py:76-78 (qkv), vlmo.py:96 (proj), timm Mlp fc1/fc2 selected by
+ * `self.mlp[route]` at vlmo.py:192/196; the residual / LayerScale adds at vlmo.py:190-196; and the
+ * autograd backward of those (dgrad, wgrad).
+ *
+ *   out[m, n] = epilogue( sum_k A(m, k) * B(n, k) )      for each group g independently.
+ *
+ * Operand storage: major 0 = "K-major": element (mn, k) at base[mn * ld + k];
+ *                  major 1 = "MN-major": element (mn, k) at base[k * ld + mn].
+ * forward  y = x W^T      : A = x  (K-major),  B = W  (K-major)
+ * dgrad    dx = dy W      : A = dy (K-major),  B = W  (MN-major)
+ * wgrad    dW = dy^T x    : A = dy (MN-major), B = x  (MN-major), contraction over the group's rows.
+ * Groups are the expert segments of the packed token buffer (text rows -> 'l', image rows -> 'v',
+ * fused rows -> 'vl'): same N/K/epilogue, per-group pointers and row counts. */
+enum MomeEpilogue {
+  MOME_EPI_STORE = 0,    /* out = acc + bias                                   (qkv, dgrad) */
+  MOME_EPI_GELU = 1,     /* out2 = z = acc + bias (pre-activation), out = gelu_erf(z)   (fc1) */
+  MOME_EPI_RESIDUAL = 2, /* out2 = b = acc + bias; out(fp32) = res + gamma * b  (proj, fc2) */
+  MOME_EPI_DGELU = 3,    /* out = acc * gelu_erf'(aux)                     (fc2 dgrad -> dz) */
+  MOME_EPI_ATOMIC = 4    /* out(fp32) += acc via red.add (split-K wgrad)                     */
+};
+
+typedef struct {
+  const void* a;
+  const void* b;
+  int64_t M;         /* rows of out for this group */
+  int64_t K;         /* contraction length for this group */
+  void* out;
+  void* out2;        /* may be NULL */
+  const float* bias; /* [N] or NULL */
+  const float* res;  /* fp32 [M, ldres] (RESIDUAL) */
+  const void* aux;   /* operand dtype [M, ldaux] (DGELU) */
+} MomeGemmGroup;
+
+typedef struct {
+  int32_t dtype;     /* operand dtype of A, B, out2, aux */
+  int32_t a_major, b_major;
+  int32_t epilogue;
+  int32_t out_dtype; /* dtype of out */
+  int32_t num_groups;
+  int32_t split_k;   /* 0 = choose automatically (only with MOME_EPI_ATOMIC) */
+  int32_t reserved;
+  int64_t N;
+  int64_t lda, ldb, ldo, ldo2, ldres, ldaux; /* in elements */
+  const float* gamma; /* [N] or NULL (RESIDUAL) */
+  MomeGemmGroup group[MOME_MAX_GROUPS];
+} MomeGemmArgs;
+
+int mome_gemm(const MomeGemmArgs* args, void* stream);
+
+/* ---- K1: masked multi-head self-attention over packed segments -----------------------------------
+ * reference: vlmo.py:79-95 (split heads, q k^T * scale, masked_fill(~mask, -inf), softmax, @ v,
+ * merge heads). qkv is the [tokens, 3*d] output of the qkv GEMM (column = s*d + h*64 + e).
+ * A sequence is up to two row ranges of the packed buffer ([text | image] after the fusion layer,
+ * one range before it): seq_desc[4*s + {0,1,2,3}] = {start0, len0, start1, len1}.
+ * key_mask[row] = 1 keeps the key, 0 excludes it; query rows are never masked. head_dim is 64. */
+int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out,
+                  float* lse, int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads,
+                  float scale, void* stream);
+/* dqkv gets every element of its [tokens, 3*d] rows written. */
+int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
+                  const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens,
+                  int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, void* stream);
+
+/* ---- K4: ITC head — similarity GEMM fused with softmax cross-entropy -------------------------------
+ * reference: objectives.py:99-108 (global-reduce logits), 166-171 (naive), 173-180 (CE + accuracy),
+ * heads.py:125-126 (L2 normalise). feats are fp32 [rows, dim]; `all_*` hold the gathered features of
+ * every rank in rank order ([world*bs, dim]); this rank's rows start at rank*bs. Outputs per
+ * direction (0 = i2t, 1 = t2i): loss_sum[dir] (sum over local rows of lse - logit[target]),
+ * correct[dir] (argmax over the local block == target), lse[dir*bs + r], and the local [bs, bs]
+ * logit block sim_local[dir] that ITM's hard-negative mining consumes (objectives.py:251-255).
+ * `temp` (= exp(itc_temp)) and `gscale` are DEVICE scalars so that no host synchronisation is needed. */
+int mome_l2norm_fwd(const void* x, int x_dtype, float* y, float* inv_norm, int64_t rows, int64_t dim,
+                    void* stream);
+int mome_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int64_t rows,
+                    int64_t dim, void* stream);
+int mome_itc_fwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t,
+                 const float* temp, int32_t bs, int32_t world, int32_t rank, int32_t dim, float* loss_sum, int32_t* correct,
+                 float* lse, float* sim_local, void* stream);
+/* Gradients of mean-CE ((i2t + t2i) / 2, each a mean over bs rows) scaled by gscale:
+ *   d_i_feat, d_t_feat [bs, dim] (local-row terms), d_all_i, d_all_t [world*bs, dim] (column terms, to
+ *   be reduce-scattered across ranks by the caller), d_temp (scalar, accumulated). */
+int mome_itc_bwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t,
+                 const float* temp, int32_t bs, int32_t world, int32_t rank, int32_t dim, const float* lse,
+                 const float* gscale,
+                 float* d_i_feat, float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream);
+
+/* ---- measurement hooks (bench.py): CUDA-event timing of every mome_gemm launch on its own stream */
+int mome_prof_enable(int on);
+/* Synchronises the recorded events; returns launches, summed milliseconds and summed FLOPs. */
+int mome_prof_read(int64_t* launches, double* ms, double* flops, int reset);
+/* total kernel launches issued by this library since load (gpu_launches claim) */
+int64_t mome_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOME_H_ */

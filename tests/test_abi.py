@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/mome.h declares;
+the product module keeps the reference's state_dict layout; the product refuses to run without CUDA."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import GOLDEN, ROOT
+from exploremultimodal_b200 import _lib, build_model, make_config
+
+
+def _ensure_built():
+    from exploremultimodal_b200 import build_ext
+    build_ext.build(verbose=False)
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'mome.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(mome_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in include/mome.h but not exported'
+    assert sorted(_lib.exported_symbols()) == declared, 'ctypes binding and header disagree'
+    lib = _lib.lib()
+    assert lib.mome_version() == _lib.ABI_VERSION
+    assert lib.mome_launch_count() == 0
+
+
+def test_struct_layout_matches_header():
+    # MomeGemmGroup: 9 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
+    assert ctypes.sizeof(_lib.GemmGroup) == 72
+    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 72
+
+
+def test_state_dict_layout_matches_reference():
+    with open(os.path.join(GOLDEN, 'state_dict_shapes.json')) as f:
+        listing = json.load(f)
+    for tag, ref in listing.items():
+        model, phase = tag.split('/')
+        names = ('vqa',) if phase == 'finetune_vqa' else ('mlm', 'itc', 'itm')
+        m = build_model(make_config(model, phase=phase, loss_names=names))
+        mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+        want = {k: s for k, s in ref['state']}
+        want.pop('transformer.txt_embeddings.position_ids', None)
+        assert mine == want, tag
+        assert sum(p.numel() for p in m.parameters()) == ref['n_params'], tag
+        assert sorted(m.no_weight_decay()) == ref['no_weight_decay'], tag
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly rather than compute on the CPU."""
+    cfg = make_config('vlmo_unit', parity=True)
+    m = build_model(cfg)
+    blk = m.transformer.blocks[0]
+    with pytest.raises((AssertionError, RuntimeError)):
+        blk(torch.zeros(1, 4, 128), None, 'v')
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'exploremultimodal_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f

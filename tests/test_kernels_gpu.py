@@ -1,0 +1,367 @@
+"""GPU: every libmome kernel, called through the C ABI, against a plain PyTorch fp32 statement of the
+same arithmetic (float64 where cheap). Tolerances: fp32 paths 1e-4 relative (north_star), bf16 paths
+2e-2 relative to the tensor norm (north_star) — in practice far tighter, asserted at 1e-2.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+def _mods():
+    from exploremultimodal_b200 import _lib as L
+    from exploremultimodal_b200 import ops
+    return L, ops
+
+
+def _dev():
+    return torch.device('cuda', 0)
+
+
+def _rand(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(_dev()).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize('rows,d', [(1, 128), (37, 768), (1000, 1024), (5000, 768), (3, 96)])
+@pytest.mark.parametrize('out_bf16', [False, True])
+def test_ln_fwd_bwd(rows, d, out_bf16):
+    L, ops = _mods()
+    x = _rand(rows, d, seed=1) * 2 + 0.5
+    w, b = 1 + 0.1 * _rand(d, seed=2), 0.1 * _rand(d, seed=3)
+    code = L.BF16 if out_bf16 else L.F32
+    y, mean, rstd = ops.ln_fwd(x, w, b, code, 1e-12)
+    ref = F.layer_norm(x.double(), (d,), w.double(), b.double(), 1e-12)
+    assert rel_err(y, ref) < (4e-3 if out_bf16 else 1e-5)
+    assert rel_err(mean, x.double().mean(1)) < 1e-5
+    if d > 1024:
+        return
+    # backward with a residual gradient
+    dy = _rand(rows, d, seed=4).to(y.dtype)
+    dres = _rand(rows, d, seed=5)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    F.layer_norm(xr, (d,), wr, br, 1e-12).backward(dy.double())
+    dw = torch.zeros(d, device=_dev())
+    db = torch.zeros(d, device=_dev())
+    dx = ops.ln_bwd(dy, x, mean, rstd, w, dres, dw, db)
+    assert rel_err(dx, xr.grad + dres.double()) < 1e-5
+    assert rel_err(dw, wr.grad) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+def test_scale_bwd_and_colsum(bf16):
+    L, ops = _mods()
+    rows, d = 777, 768
+    dt = torch.bfloat16 if bf16 else torch.float32
+    dx = _rand(rows, d, seed=1)
+    branch = _rand(rows, d, seed=2).to(dt)
+    gamma = 0.1 * (1 + 0.2 * _rand(d, seed=3))
+    dbranch = torch.empty(rows, d, dtype=dt, device=_dev())
+    dgamma = torch.zeros(d, device=_dev())
+    dbias = torch.zeros(d, device=_dev())
+    L.check(L.lib().mome_scale_bwd(dx.data_ptr(), branch.data_ptr(), L.dtype_code(branch), gamma.data_ptr(),
+                                   dbranch.data_ptr(), L.dtype_code(branch), dgamma.data_ptr(), dbias.data_ptr(), rows, d,
+                                   L.stream()), 'scale_bwd')
+    want = dx.double() * gamma.double()
+    assert rel_err(dbranch, want) < (4e-3 if bf16 else 1e-6)
+    assert rel_err(dgamma, (dx.double() * branch.double()).sum(0)) < 1e-4
+    assert rel_err(dbias, dbranch.double().sum(0)) < 1e-4
+    out = torch.zeros(d, device=_dev())
+    ops.colsum(branch, out)
+    assert rel_err(out, branch.double().sum(0)) < 1e-4
+    out2 = torch.zeros(d, device=_dev())
+    ops.colsum(branch, out2, first_row=100, rows=300)
+    assert rel_err(out2, branch[100:400].double().sum(0)) < 1e-4
+
+
+def test_cast_bf16():
+    L, ops = _mods()
+    src = _rand(1000 * 777 + 3, seed=9)
+    n = src.numel() // 4 * 4
+    src = src[:n].contiguous()
+    dst = torch.empty(n, dtype=torch.bfloat16, device=_dev())
+    ops.cast_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def _gemm_ref(a, b, a_major, b_major):
+    A = a.double() if a_major == 0 else a.double().t()
+    Bm = b.double() if b_major == 0 else b.double().t()
+    return A @ Bm.t()
+
+
+def _gelu_grad(z):
+    z = z.double()
+    return 0.5 * (1 + torch.erf(z / math.sqrt(2))) + z * torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
+
+
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 128, 64), (300, 384, 128), (1000, 768, 768), (237 * 3, 2304, 768), (520, 3072, 768), (129, 768, 3072),
+    (64, 256, 200),
+]
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('majors', [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
+def test_gemm_store(bf16, majors, M, N, K):
+    L, ops = _mods()
+    a_major, b_major = majors
+    if bf16 and a_major == 1 and (M % 8 or K % 8):
+        pytest.skip('TMA pitch must be a multiple of 16 bytes')
+    dt = torch.bfloat16 if bf16 else torch.float32
+    code = L.BF16 if bf16 else L.F32
+    a = _rand(*((M, K) if a_major == 0 else (K, M)), dtype=dt, seed=1)
+    b = _rand(*((N, K) if b_major == 0 else (K, N)), dtype=dt, seed=2)
+    if bf16 and ((a.shape[1] % 8) or (b.shape[1] % 8)):
+        pytest.skip('TMA pitch must be a multiple of 16 bytes')
+    bias = _rand(N, seed=3)
+    ref = _gemm_ref(a, b, a_major, b_major) + bias.double()
+    for out_code in ([L.BF16, L.F32] if bf16 else [L.F32]):
+        out = torch.full((M, N), float('nan'), dtype=torch.bfloat16 if out_code == L.BF16 else torch.float32, device=_dev())
+        ops.gemm(code, a_major, b_major, L.EPI_STORE, out_code, N, a.shape[1], b.shape[1], N,
+                 [dict(a=a.data_ptr(), b=b.data_ptr(), M=M, K=K, out=out.data_ptr(), bias=bias.data_ptr())])
+        torch.cuda.synchronize()
+        tol = 5e-3 if out_code == L.BF16 else (1e-5 if not bf16 else 1e-5)
+        assert rel_err(out, ref) < tol, (majors, M, N, K, out_code)
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+def test_gemm_atomic_wgrad_grouped(bf16):
+    """dW_g += dy_g^T x_g for two expert groups of different row counts (split-K, red.add)."""
+    L, ops = _mods()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    code = L.BF16 if bf16 else L.F32
+    es = 2 if bf16 else 4
+    rows = [40 * 7, 197 * 7]
+    n_out, n_in = 512, 128
+    dy = _rand(sum(rows), n_out, dtype=dt, seed=1)
+    x = _rand(sum(rows), n_in, dtype=dt, seed=2)
+    outs = [torch.zeros(n_out, n_in, device=_dev()) for _ in rows]
+    groups, s = [], 0
+    for r, o in zip(rows, outs):
+        groups.append(dict(a=dy.data_ptr() + s * n_out * es, b=x.data_ptr() + s * n_in * es, M=n_out, K=r, out=o.data_ptr()))
+        s += r
+    ops.gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, n_in, n_out, n_in, n_in, groups)
+    s = 0
+    for r, o in zip(rows, outs):
+        ref = dy[s:s + r].double().t() @ x[s:s + r].double()
+        assert rel_err(o, ref) < 1e-5, r
+        s += r
+    # accumulation: a second launch doubles the result
+    ops.gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, n_in, n_out, n_in, n_in, groups)
+    assert rel_err(outs[0], 2 * (dy[:rows[0]].double().t() @ x[:rows[0]].double())) < 1e-5
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+def test_gemm_gelu_residual_dgelu_grouped(bf16):
+    """The three fused epilogues on a two-group (text 'l' rows, image 'v' rows) problem."""
+    L, ops = _mods()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    code = L.BF16 if bf16 else L.F32
+    es = 2 if bf16 else 4
+    d, hid = 128, 512
+    rows = [36, 17 * 5]
+    tot = sum(rows)
+    h = _rand(tot, d, dtype=dt, seed=1)
+    w1 = [_rand(hid, d, dtype=dt, seed=10 + i, scale=0.1) for i in range(2)]
+    b1 = [_rand(hid, seed=20 + i, scale=0.1) for i in range(2)]
+    w2 = [_rand(d, hid, dtype=dt, seed=30 + i, scale=0.1) for i in range(2)]
+    b2 = [_rand(d, seed=40 + i, scale=0.1) for i in range(2)]
+    gamma = 0.1 * (1 + 0.2 * _rand(d, seed=5))
+    res = _rand(tot, d, seed=6)
+    z = torch.empty(tot, hid, dtype=dt, device=_dev())
+    u = torch.empty(tot, hid, dtype=dt, device=_dev())
+    x2 = torch.empty(tot, d, device=_dev())
+    br = torch.empty(tot, d, dtype=dt, device=_dev())
+    g1, g2, s = [], [], 0
+    for i, r in enumerate(rows):
+        g1.append(dict(a=h.data_ptr() + s * d * es, b=w1[i].data_ptr(), M=r, K=d, out=u.data_ptr() + s * hid * es,
+                       out2=z.data_ptr() + s * hid * es, bias=b1[i].data_ptr()))
+        g2.append(dict(a=u.data_ptr() + s * hid * es, b=w2[i].data_ptr(), M=r, K=hid, out=x2.data_ptr() + s * d * 4,
+                       out2=br.data_ptr() + s * d * es, bias=b2[i].data_ptr(), res=res.data_ptr() + s * d * 4))
+        s += r
+    ops.gemm(code, 0, 0, L.EPI_GELU, code, hid, d, d, hid, g1, ldo2=hid)
+    ops.gemm(code, 0, 0, L.EPI_RESIDUAL, L.F32, d, hid, hid, d, g2, ldo2=d, ldres=d, gamma=gamma.data_ptr())
+    tol = 6e-3 if bf16 else 1e-5
+    s = 0
+    for i, r in enumerate(rows):
+        zr = h[s:s + r].double() @ w1[i].double().t() + b1[i].double()
+        assert rel_err(z[s:s + r], zr) < tol
+        assert rel_err(u[s:s + r], F.gelu(z[s:s + r].double())) < tol
+        brr = u[s:s + r].double() @ w2[i].double().t() + b2[i].double()
+        assert rel_err(br[s:s + r], brr) < tol
+        assert rel_err(x2[s:s + r], res[s:s + r].double() + gamma.double() * br[s:s + r].double()) < 1e-5
+        s += r
+    # dz = (dy @ W2) * gelu'(z)
+    dy = _rand(tot, d, dtype=dt, seed=7)
+    dz = torch.empty(tot, hid, dtype=dt, device=_dev())
+    g3, s = [], 0
+    for i, r in enumerate(rows):
+        g3.append(dict(a=dy.data_ptr() + s * d * es, b=w2[i].data_ptr(), M=r, K=d, out=dz.data_ptr() + s * hid * es,
+                       aux=z.data_ptr() + s * hid * es))
+        s += r
+    ops.gemm(code, 0, 1, L.EPI_DGELU, code, hid, d, hid, hid, g3, ldaux=hid)
+    s = 0
+    for i, r in enumerate(rows):
+        ref = (dy[s:s + r].double() @ w2[i].double()) * _gelu_grad(z[s:s + r])
+        assert rel_err(dz[s:s + r], ref) < tol
+        s += r
+
+
+def test_gemm_rejects_bad_arguments():
+    L, ops = _mods()
+    a = _rand(8, 8)
+    with pytest.raises(RuntimeError, match='num_groups'):
+        ops.gemm(L.F32, 0, 0, L.EPI_STORE, L.F32, 8, 8, 8, 8, [])
+    with pytest.raises(RuntimeError):
+        ops.gemm(L.BF16, 0, 0, L.EPI_STORE, L.BF16, 20, 8, 8, 20,
+                 [dict(a=a.data_ptr(), b=a.data_ptr(), M=8, K=8, out=a.data_ptr())])
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, seqs, key_mask, H, scale):
+    """Plain statement of reference vlmo.py:79-95 per packed sequence. Returns out [tokens, d]."""
+    tokens, d3 = qkv.shape
+    d = d3 // 3
+    out = torch.zeros(tokens, d, dtype=qkv.dtype, device=qkv.device)
+    for (s0, l0, s1, l1) in seqs:
+        rows = torch.cat([torch.arange(s0, s0 + l0), torch.arange(s1, s1 + l1)]).to(qkv.device)
+        x = qkv[rows]
+        n = rows.numel()
+        q, k, v = x.view(n, 3, H, 64).permute(1, 2, 0, 3)
+        s = (q @ k.transpose(-1, -2)) * scale
+        s = s.masked_fill(~key_mask[rows].bool()[None, None, :], float('-inf'))
+        o = torch.softmax(s, -1) @ v
+        out[rows] = o.permute(1, 0, 2).reshape(n, d)
+    return out
+
+
+ATTN_CASES = [
+    # (list of (start0, len0, start1, len1), tokens, heads)
+    ([(0, 40, 0, 0), (40, 40, 0, 0)], 80, 2),
+    ([(0, 12, 36, 17), (12, 12, 53, 17), (24, 12, 70, 17)], 87, 2),
+    ([(0, 197, 0, 0)], 197, 3),
+    ([(0, 40, 80, 197), (40, 40, 277, 197)], 80 + 394, 12),
+    ([(0, 40, 40, 901)], 941, 2),
+]
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('case', range(len(ATTN_CASES)))
+def test_attention_fwd_bwd(bf16, case):
+    L, ops = _mods()
+    seqs, tokens, H = ATTN_CASES[case]
+    d = 64 * H
+    dt = torch.bfloat16 if bf16 else torch.float32
+    qkv = _rand(tokens, 3 * d, dtype=dt, seed=case + 1)
+    g = torch.Generator().manual_seed(100 + case)
+    key_mask = (torch.rand(tokens, generator=g) > 0.25).to(torch.uint8)
+    for (s0, l0, s1, l1) in seqs:
+        key_mask[s0] = 1  # CLS is never padded
+    key_mask = key_mask.to(_dev())
+    desc = torch.tensor(seqs, dtype=torch.int32, device=_dev())
+    lay = ops.PackedLayout(tokens, [(0, tokens, 'vl')], desc, len(seqs), max(l0 + l1 for (_, l0, _, l1) in seqs))
+    scale = 0.125
+    out, lse = ops.attn_fwd(qkv, lay, key_mask, H, scale)
+    qd = qkv.double().requires_grad_(True)
+    ref = _attn_ref(qd, seqs, key_mask, H, scale)
+    tol = BF16_TOL if bf16 else FP32_TOL
+    assert rel_err(out, ref) < tol
+    dout = _rand(tokens, d, dtype=dt, seed=50 + case)
+    ref.backward(dout.double())
+    dqkv = ops.attn_bwd(qkv, out, dout, lay, key_mask, lse, H, scale)
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (('dq', slice(0, d)), ('dk', slice(d, 2 * d)), ('dv', slice(2 * d, 3 * d))):
+        assert rel_err(dqkv[:, sl], qd.grad[:, sl]) < (2e-2 if bf16 else FP32_TOL), name
+
+
+def test_attention_no_mask_pointer():
+    L, ops = _mods()
+    seqs, tokens, H = ATTN_CASES[1]
+    qkv = _rand(tokens, 3 * 64 * H, seed=3)
+    desc = torch.tensor(seqs, dtype=torch.int32, device=_dev())
+    lay = ops.PackedLayout(tokens, [(0, tokens, 'vl')], desc, len(seqs), 29)
+    out, _ = ops.attn_fwd(qkv, lay, None, H, 0.125)
+    ref = _attn_ref(qkv.double(), seqs, torch.ones(tokens, dtype=torch.uint8, device=_dev()), H, 0.125)
+    assert rel_err(out, ref) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------ ITC
+def _itc_ref(i_feat, t_feat, all_i, all_t, temp, rank):
+    bs = i_feat.shape[0]
+    tgt = torch.arange(bs, device=i_feat.device) + rank * bs
+    sim_i2t = i_feat @ all_t.t() * temp
+    sim_t2i = t_feat @ all_i.t() * temp
+    l1 = F.cross_entropy(sim_i2t, tgt, reduction='sum')
+    l2 = F.cross_entropy(sim_t2i, tgt, reduction='sum')
+    return l1, l2, sim_i2t, sim_t2i
+
+
+@pytest.mark.parametrize('bs,world,rank,dim', [(3, 1, 0, 32), (16, 1, 0, 256), (8, 4, 2, 256), (130, 8, 7, 256), (512, 8, 3, 256)])
+def test_itc_fwd_bwd(bs, world, rank, dim):
+    L, ops = _mods()
+    from exploremultimodal_b200 import objectives  # noqa: F401  (binding only)
+    all_i = F.normalize(_rand(world * bs, dim, seed=1), dim=-1).contiguous()
+    all_t = F.normalize(_rand(world * bs, dim, seed=2) + 0.5 * all_i, dim=-1).contiguous()
+    i_feat = all_i[rank * bs:(rank + 1) * bs].contiguous()
+    t_feat = all_t[rank * bs:(rank + 1) * bs].contiguous()
+    temp = torch.tensor([14.2857], device=_dev())
+    dev = _dev()
+    loss_sum = torch.empty(2, device=dev)
+    correct = torch.empty(2, dtype=torch.int32, device=dev)
+    lse = torch.empty(2 * bs, device=dev)
+    sim_local = torch.empty(2, bs, bs, device=dev)
+    L.check(L.lib().mome_itc_fwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(), temp.data_ptr(),
+                                 bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(), lse.data_ptr(),
+                                 sim_local.data_ptr(), L.stream()), 'itc_fwd')
+    fi, ft = i_feat.double().requires_grad_(True), t_feat.double().requires_grad_(True)
+    ai, at = all_i.double().requires_grad_(True), all_t.double().requires_grad_(True)
+    tp = temp.double().requires_grad_(True)
+    l1, l2, s1, s2 = _itc_ref(fi, ft, ai, at, tp, rank)
+    assert rel_err(loss_sum, torch.stack([l1, l2])) < 1e-5
+    assert rel_err(sim_local[0], s1[:, rank * bs:(rank + 1) * bs]) < 1e-5
+    assert rel_err(sim_local[1], s2[:, rank * bs:(rank + 1) * bs]) < 1e-5
+    tgt = torch.arange(bs, device=dev)
+    assert int(correct[0]) == int((s1[:, rank * bs:(rank + 1) * bs].argmax(1) == tgt).sum())
+    assert int(correct[1]) == int((s2[:, rank * bs:(rank + 1) * bs].argmax(1) == tgt).sum())
+    gscale = torch.tensor([0.7], device=dev)
+    ((l1 + l2) / (2 * bs) * 0.7).backward()
+    d_i, d_t = torch.empty_like(i_feat), torch.empty_like(t_feat)
+    d_ai, d_at = torch.empty_like(all_i), torch.empty_like(all_t)
+    d_temp = torch.zeros(1, device=dev)
+    L.check(L.lib().mome_itc_bwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(), temp.data_ptr(),
+                                 bs, world, rank, dim, lse.data_ptr(), gscale.data_ptr(), d_i.data_ptr(), d_t.data_ptr(),
+                                 d_ai.data_ptr(), d_at.data_ptr(), d_temp.data_ptr(), L.stream()), 'itc_bwd')
+    assert rel_err(d_i, fi.grad) < 1e-4
+    assert rel_err(d_t, ft.grad) < 1e-4
+    assert rel_err(d_ai, ai.grad) < 1e-4
+    assert rel_err(d_at, at.grad) < 1e-4
+    assert rel_err(d_temp, tp.grad) < 1e-4
+
+
+def test_l2norm():
+    from exploremultimodal_b200.heads import _L2Normalize
+    for dt in (torch.float32, torch.bfloat16):
+        x = _rand(33, 256, dtype=dt, seed=4).requires_grad_(True)
+        y = _L2Normalize.apply(x)
+        xr = x.detach().double().requires_grad_(True)
+        yr = F.normalize(xr, dim=-1)
+        assert rel_err(y, yr) < 1e-5
+        dy = _rand(33, 256, seed=5)
+        y.backward(dy)
+        yr.backward(dy.double())
+        assert rel_err(x.grad, xr.grad) < (1e-2 if dt == torch.bfloat16 else 1e-5)

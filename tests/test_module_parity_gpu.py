@@ -1,0 +1,161 @@
+"""GPU: the product module (exploremultimodal_b200.build_model, libmome kernels through the C ABI)
+against (1) the committed golden fixtures produced by the unmodified reference and (2) the CPU oracle
+run on the same seeded inputs. Routing is compared bit-exactly; activations, losses and gradients at
+1e-4 (fp32 path) and 2e-2 (bf16 path) relative, the tolerances north_star states.
+"""
+import pytest
+import torch
+
+from helpers import case_batch, case_config, check_summary, load_golden, oracle_state, rel_err
+from exploremultimodal_b200 import build_model, make_config
+from exploremultimodal_b200.synthetic import make_batch, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32': 1e-4, 'bf16': 2e-2}
+
+
+def _build(cfg, precision):
+    from exploremultimodal_b200 import objectives
+    cfg.model.precision = precision
+    model = build_model(cfg)
+    shapes = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(synth_state_dict(shapes, cfg.model.init_values), strict=True)
+    model.cuda().train()
+    model.itm_negative_picker = objectives.pick_negatives_argmax
+    return model
+
+
+def _to_cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def _expected_groups(route_log, T):
+    """Expand the reference's ordered (layer, route, rows, tokens) Block calls of ONE module forward
+    into the multiset of (layer, route, n_rows_total) expert assignments."""
+    out = {}
+    for (layer, route, rows, toks) in route_log:
+        out.setdefault((layer, route, rows * toks), 0)
+        out[(layer, route, rows * toks)] += 1
+    return out
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa'])
+def test_module_matches_reference_golden(name, precision):
+    gold = load_golden(name)
+    cfg = case_config(gold['case'])
+    model = _build(cfg, precision)
+    batch = _to_cuda(case_batch(cfg, gold['case']))
+    model.transformer.route_log = []
+    out = model(batch)
+    loss = sum(v for k, v in out.items() if 'task_loss' in k)
+    loss.backward()
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+
+    # ---- routing, bit exact: every (layer, expert, rows) assignment of the reference happens here too
+    mine = {}
+    for (layer, route, first, rows) in model.transformer.route_log:
+        mine[(layer, route, rows)] = mine.get((layer, route, rows), 0) + 1
+    assert mine == _expected_groups(gold['route_log'], cfg.model.max_text_len)
+
+    # ---- losses and logits
+    assert abs(float(loss) - gold['total_loss']) <= tol * abs(gold['total_loss']), (float(loss), gold['total_loss'])
+    for k, v in gold['losses'].items():
+        assert abs(float(out[k]) - v) <= tol * max(abs(v), 1e-3), (k, float(out[k]), v)
+    bs = gold['case']['bs']
+    for k in ('sim_i2t', 'sim_t2i'):
+        if k in gold:
+            assert rel_err(out[k], gold[k][:, :bs]) < tol, k
+    for k in ('itm_logits', 'vqa_logits'):
+        if k in gold:
+            assert rel_err(out[k].float(), gold[k]) < tol, k
+    if 'mlm_logits' in gold:
+        n = gold['mlm_logits'].shape[0]
+        assert int(out['mlm_count']) == n
+        assert rel_err(out['mlm_logits'][:n].float(), gold['mlm_logits']) < tol
+    for k, v in gold['scalars'].items():
+        if 'count' in k and k in out:
+            assert int(out[k]) == int(v), k
+
+    # ---- gradients of every parameter the reference produced one for
+    params = dict(model.named_parameters())
+    for k, g in gold['grads'].items():
+        key = 'transformer.txt_embeddings.word_embeddings.weight' if k == 'mlm_head.decoder.weight' else k
+        assert params[key].grad is not None, k
+        check_summary(k, params[key].grad, g, tol * (3 if precision == 'bf16' else 1), what='grad ')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_backbone_activations_match_oracle(precision):
+    """Every infer mode, ragged text lengths: co_feats / cls_feats against the CPU oracle."""
+    from oracle import mome_oracle as O
+    cfg = make_config('vlmo_unit', parity=True)
+    model = _build(cfg, precision)
+    sd = oracle_state(cfg, requires_grad=False)
+    batch = make_batch(cfg, 5, seed=321, lengths='realistic')
+    cb = _to_cuda(batch)
+    for mode in ('img-txt', 'img_only', 'txt_only'):
+        with torch.no_grad():
+            mine = model.infer(cb, infer_mode=mode)
+            want = O.infer(sd, cfg, batch, infer_mode=mode)
+        assert rel_err(mine['co_feats'], want['co_feats']) < TOL[precision], mode
+        assert rel_err(mine['cls_feats'].float(), want['cls_feats']) < TOL[precision], mode
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_block_api_matches_oracle(precision):
+    """Reference `Block.forward(x, mask, route)` signature on its own, forward and backward."""
+    from oracle import mome_oracle as O
+    cfg = make_config('vlmo_unit', parity=True)
+    model = _build(cfg, precision)
+    sd = oracle_state(cfg, requires_grad=False)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 17, cfg.model.embed_dim, generator=g)
+    mask = (torch.rand(3, 17, generator=g) > 0.3).long()
+    mask[:, 0] = 1
+    for layer, route in ((0, 'v'), (1, 'l'), (3, 'vl')):
+        xr = x.clone().requires_grad_(True)
+        want = O.block(sd, cfg, layer, xr, mask, route)
+        want.square().sum().backward()
+        xc = x.cuda().requires_grad_(True)
+        got, attn = model.transformer.blocks[layer](xc, mask.cuda(), route)
+        assert attn is None
+        got.square().sum().backward()
+        assert rel_err(got, want) < TOL[precision], (layer, route)
+        assert rel_err(xc.grad, xr.grad) < TOL[precision] * 2, (layer, route)
+
+
+def test_itc_matches_oracle_naive_branch():
+    from oracle import mome_oracle as O
+    from exploremultimodal_b200 import objectives
+    g = torch.Generator().manual_seed(3)
+    i = torch.nn.functional.normalize(torch.randn(9, 32, generator=g), dim=-1)
+    t = torch.nn.functional.normalize(torch.randn(9, 32, generator=g), dim=-1)
+    temp = torch.tensor(14.2857)
+    want = O.itc_loss_from_feats(i, t, temp, False)
+    got = objectives.itc_loss_from_feats(i.cuda(), t.cuda(), temp.cuda(), False)
+    for k in ('itc_task_loss', 'i2t_Loss', 't2i_Loss', 'itc_i2t_mean_acc', 'itc_t2i_mean_acc'):
+        assert abs(float(got[k]) - float(want[k])) < 1e-5 * max(1.0, abs(float(want[k]))), k
+    assert rel_err(got['sim_i2t'], want['sim_i2t']) < 1e-5
+    assert rel_err(got['sim_t2i'], want['sim_t2i']) < 1e-5
+
+
+def test_weight_cache_follows_optimizer_updates():
+    """bf16 weight copies must be refreshed after an in-place parameter update."""
+    cfg = make_config('vlmo_unit', parity=True)
+    model = _build(cfg, 'bf16')
+    blk = model.transformer.blocks[0]
+    x = torch.randn(2, 9, cfg.model.embed_dim, device='cuda')
+    y0, _ = blk(x, None, 'v')
+    with torch.no_grad():
+        blk.mlp['v'].fc2.weight.mul_(0.0)
+        blk.mlp['v'].fc2.bias.mul_(0.0)
+    y1, _ = blk(x, None, 'v')
+    assert rel_err(y1, y0) > 1e-3
+    with torch.no_grad():
+        blk.attn.proj.weight.mul_(0.0)
+        blk.attn.proj.bias.mul_(0.0)
+    y2, _ = blk(x, None, 'v')
+    assert rel_err(y2, x) < 1e-6  # both branches contribute exactly zero now
