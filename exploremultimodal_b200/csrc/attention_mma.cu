@@ -1,21 +1,502 @@
-// K1 (bf16 path): tensor-core attention. Placeholder revision: forwards to the CUDA-core kernels
-// until the mma kernels land (same results, lower throughput).
+// K1 (bf16 path): flash-style masked multi-head self-attention over packed segments on the tensor
+// cores (mma.sync m16n8k16, bf16 in / fp32 accumulate), head_dim 64.
+//
+// A CTA of 4 warps owns a 64-row tile of one (sequence, head): 64 queries in the forward and dq
+// kernels, 64 keys in the dk/dv kernel; every warp owns 16 of those rows, so each product in the
+// kernel is a per-warp 16 x 64 x 64 GEMM whose A operand lives in registers and whose B operand is
+// a 64 x 64 bf16 tile in XOR-swizzled shared memory (ldmatrix, bank-conflict free). The opposite
+// side streams through a double-buffered cp.async pipeline. Softmax is online (running max / sum in
+// the exp2 domain); probabilities never leave registers. Sequences are given as up to two row
+// ranges of the packed token buffer ([text | image] after the fusion layer), keys are dropped by
+// key_mask, query rows are never masked (reference vlmo.py:89-91).
+//
+// Backward = dq kernel (per query tile: S, dP, dQ) + dk/dv kernel (per key tile: S^T, dP^T, dV, dK),
+// recomputing probabilities from the saved log-sum-exp; no atomics, deterministic.
+//
+// Replaces: reference vlmo.py:79-95 and its autograd backward. The tcgen05 variant is future work:
+// at N <= 237 the whole (sequence, head) problem is 4 tiles and the kernel is latency bound.
 #include "common.cuh"
+#include "ptx.cuh"
+#include "vec.cuh"
 
 namespace mome {
-int attn_fwd_simt_dispatch(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse,
-                           int num_seqs, int max_seq_len, int H, float scale, cudaStream_t stream);
-int attn_bwd_simt_dispatch(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
-                           const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len,
-                           int H, float scale, cudaStream_t stream);
+
+namespace {
+
+constexpr int kT = 64;                  // tile rows (queries or keys) and head_dim
+constexpr int kThreads = 128;
+constexpr int kTileBytes = kT * kT * 2;  // 8 KiB
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct Seq {
+  int start0, len0, start1, len1;
+};
+__device__ __forceinline__ Seq load_seq(const int32_t* seq_desc, int s) {
+  const int4 v = *reinterpret_cast<const int4*>(seq_desc + 4 * s);
+  return Seq{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ long long seq_row(const Seq& sd, int i) {
+  return i < sd.len0 ? static_cast<long long>(sd.start0) + i : static_cast<long long>(sd.start1) + (i - sd.len0);
+}
+
+// byte address of 16-byte chunk `chunk` of row `row` in a swizzled 64 x 64 bf16 tile
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// rows [t0, t0 + 64) of the sequence, 64 bf16 starting at `gbase` (column offset applied) -> swizzled tile
+__device__ __forceinline__ void load_tile_async(uint8_t* tile, const __nv_bfloat16* gbase, long long ld, const Seq& sd, int n,
+                                                int t0) {
+#pragma unroll
+  for (int c = threadIdx.x; c < kT * 8; c += kThreads) {
+    const int r = c >> 3, ch = c & 7;
+    const bool valid = t0 + r < n;
+    const __nv_bfloat16* src = gbase + seq_row(sd, valid ? t0 + r : 0) * ld + ch * 8;
+    cp_async_16(tile + r * 128 + ((ch ^ (r & 7)) << 4), src, valid);
+  }
+}
+
+// A fragments (4 k-steps) of the warp's 16 rows [r0, r0 + 16) of a swizzled tile
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], uint32_t tile, int r0) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(a[ks], tile_addr(tile, r0 + (lane & 15), ks * 2 + (lane >> 4)));
+}
+
+// acc[16 x 64] += A[16 x 64] * B, B(n, k) = tile[n][k] (TRANS = false) or tile[k][n] (TRANS = true)
+template <bool TRANS>
+__device__ __forceinline__ void warp_gemm(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile) {
+  const int lane = threadIdx.x & 31;
+  const int m = lane >> 3, l8 = lane & 7;
+  if (!TRANS) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b[4];
+        ldmatrix_x4(b, tile_addr(tile, p * 16 + (m >> 1) * 8 + l8, ks * 2 + (m & 1)));
+        mma_bf16_16816(acc[2 * p], a[ks], b[0], b[1]);
+        mma_bf16_16816(acc[2 * p + 1], a[ks], b[2], b[3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, tile_addr(tile, ks * 16 + (m & 1) * 8 + l8, p * 2 + (m >> 1)));
+        mma_bf16_16816(acc[2 * p], a[ks], b[0], b[1]);
+        mma_bf16_16816(acc[2 * p + 1], a[ks], b[2], b[3]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+}
+
+// accumulator (16 x 64, C layout) -> bf16 A fragments for the next GEMM
+__device__ __forceinline__ void acc_to_a(uint32_t (&a)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j][0] = pack_bf16(c[2 * j][0], c[2 * j][1]);
+    a[j][1] = pack_bf16(c[2 * j][2], c[2 * j][3]);
+    a[j][2] = pack_bf16(c[2 * j + 1][0], c[2 * j + 1][1]);
+    a[j][3] = pack_bf16(c[2 * j + 1][2], c[2 * j + 1][3]);
+  }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// Write the warp's 16 x 64 accumulator (times `mul` per row) as bf16 rows of the packed buffer:
+// staged through the warp's own 16 rows of a swizzled tile so that global stores are 16-byte wide.
+__device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float mul0, float mul1, uint8_t* tile, int r0,
+                                                __nv_bfloat16* gbase, long long ld, const Seq& sd, int n, int t0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    // columns nt*8 + 2t, +1  -> chunk nt, byte offset 4t within the chunk
+    *reinterpret_cast<uint32_t*>(tile + (r0 + g) * 128 + ((nt ^ ((r0 + g) & 7)) << 4) + 4 * t) = pack_bf16(acc[nt][0] * mul0, acc[nt][1] * mul0);
+    *reinterpret_cast<uint32_t*>(tile + (r0 + g + 8) * 128 + ((nt ^ ((r0 + g + 8) & 7)) << 4) + 4 * t) = pack_bf16(acc[nt][2] * mul1, acc[nt][3] * mul1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = lane; c < 16 * 8; c += 32) {
+    const int r = r0 + (c >> 3), ch = c & 7;
+    if (t0 + r < n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4));
+      *reinterpret_cast<uint4*>(gbase + seq_row(sd, t0 + r) * ld + ch * 8) = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask, const Seq& sd, int n, int t0) {
+  if (threadIdx.x < kT) {
+    const int j = t0 + threadIdx.x;
+    keep[threadIdx.x] = (j < n) && (key_mask == nullptr || key_mask[seq_row(sd, j)] != 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- forward
+// smem: Q | K0 | K1 | V0 | V1 tiles, keep[2][64]
+constexpr int kFwdSmem = 5 * kTileBytes + 2 * kT;
+
+__global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seq_desc,
+                                                                const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out,
+                                                                float* __restrict__ lse, int H, int max_seq_len, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + kTileBytes;
+  uint8_t* Vs = smem + 3 * kTileBytes;
+  uint8_t* keep = smem + 5 * kTileBytes;
+  const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kT;
+  const Seq sd = load_seq(seq_desc, s);
+  const int n = sd.len0 + sd.len1;
+  if (q0 >= n) return;
+  const int d = H * kT;
+  const long long ld = 3LL * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ntiles = (n + kT - 1) / kT;
+
+  load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
+  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, 0);
+  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, 0);
+  cp_async_commit();
+  load_keep(keep, key_mask, sd, n, 0);
+
+  uint32_t qf[4][4];
+  float o[8][4];
+  zero_acc(o);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sl2 = scale * kLog2e;
+
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ntiles) {
+      load_tile_async(Ks + (buf ^ 1) * kTileBytes, qkv + d + h * kT, ld, sd, n, (kt + 1) * kT);
+      load_tile_async(Vs + (buf ^ 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, (kt + 1) * kT);
+      load_keep(keep + (buf ^ 1) * kT, key_mask, sd, n, (kt + 1) * kT);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (kt == 0) load_a_frags(qf, smem_u32(Qs), warp * 16);
+
+    float sacc[8][4];
+    zero_acc(sacc);
+    warp_gemm<false>(sacc, qf, smem_u32(Ks + buf * kTileBytes));
+    const uint8_t* kp = keep + buf * kT;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
+      sacc[nt][0] = k0 ? sacc[nt][0] * sl2 : -INFINITY;
+      sacc[nt][1] = k1 ? sacc[nt][1] * sl2 : -INFINITY;
+      sacc[nt][2] = k0 ? sacc[nt][2] * sl2 : -INFINITY;
+      sacc[nt][3] = k1 ? sacc[nt][3] * sl2 : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    mx0 = quad_max(mx0);
+    mx1 = quad_max(mx1);
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;  // all keys masked so far
+    const float c0 = exp2f(m0 - ms0), c1 = exp2f(m1 - ms1);
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sacc[nt][0] = exp2f(sacc[nt][0] - ms0);
+      sacc[nt][1] = exp2f(sacc[nt][1] - ms0);
+      sacc[nt][2] = exp2f(sacc[nt][2] - ms1);
+      sacc[nt][3] = exp2f(sacc[nt][3] - ms1);
+      rs0 += sacc[nt][0] + sacc[nt][1];
+      rs1 += sacc[nt][2] + sacc[nt][3];
+    }
+    l0 = l0 * c0 + quad_sum(rs0);
+    l1 = l1 * c1 + quad_sum(rs1);
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+    }
+    uint32_t pf[4][4];
+    acc_to_a(pf, sacc);
+    warp_gemm<true>(o, pf, smem_u32(Vs + buf * kTileBytes));
+    __syncthreads();  // everyone is done with buffer `buf` before it is refilled
+  }
+  cp_async_wait<0>();
+
+  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  store_rows_bf16(o, inv0, inv1, Qs, warp * 16, out + h * kT, static_cast<long long>(d), sd, n, q0);
+  if (t == 0) {
+    const long long base = (static_cast<long long>(s) * H + h) * max_seq_len + q0 + warp * 16;
+    if (q0 + warp * 16 + g < n) lse[base + g] = l0 > 0.f ? (m0 + log2f(l0)) * kLn2 : -INFINITY;
+    if (q0 + warp * 16 + g + 8 < n) lse[base + g + 8] = l1 > 0.f ? (m1 + log2f(l1)) * kLn2 : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward: dq (+ delta)
+// smem: Q | dO | K0 | K1 | V0 | V1, keep[2][64], delta[64] floats
+constexpr int kDqSmem = 6 * kTileBytes + 2 * kT + kT * 4;
+
+__global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                                                                   const __nv_bfloat16* __restrict__ dout, const int32_t* __restrict__ seq_desc,
+                                                                   const uint8_t* __restrict__ key_mask, const float* __restrict__ lse,
+                                                                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ delta_ws, int H,
+                                                                   int max_seq_len, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Qs = smem;
+  uint8_t* Gs = smem + kTileBytes;
+  uint8_t* Ks = smem + 2 * kTileBytes;
+  uint8_t* Vs = smem + 4 * kTileBytes;
+  uint8_t* keep = smem + 6 * kTileBytes;
+  float* delta_s = reinterpret_cast<float*>(smem + 6 * kTileBytes + 2 * kT);
+  const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kT;
+  const Seq sd = load_seq(seq_desc, s);
+  const int n = sd.len0 + sd.len1;
+  if (q0 >= n) return;
+  const int d = H * kT;
+  const long long ld = 3LL * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ntiles = (n + kT - 1) / kT;
+  const long long stat0 = (static_cast<long long>(s) * H + h) * max_seq_len;
+
+  // O goes through the second K buffer (free until tile 1 is prefetched) to form delta = rowsum(dO * O)
+  load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
+  load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, q0);
+  load_tile_async(Ks + kTileBytes, out + h * kT, static_cast<long long>(d), sd, n, q0);
+  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, 0);
+  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, 0);
+  cp_async_commit();
+  load_keep(keep, key_mask, sd, n, 0);
+  cp_async_wait<0>();
+  __syncthreads();
+  {
+    // two threads per row, 32 columns (4 chunks) each
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ch = half * 4 + c;
+      const uint4 a = *reinterpret_cast<const uint4*>(Gs + r * 128 + ((ch ^ (r & 7)) << 4));
+      const uint4 b = *reinterpret_cast<const uint4*>(Ks + kTileBytes + r * 128 + ((ch ^ (r & 7)) << 4));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+        const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+        acc += fa.x * fb.x + fa.y * fb.y;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      delta_s[r] = acc;
+      if (q0 + r < n) delta_ws[stat0 + q0 + r] = acc;
+    }
+  }
+  __syncthreads();
+
+  uint32_t qf[4][4], gf[4][4];
+  load_a_frags(qf, smem_u32(Qs), warp * 16);
+  load_a_frags(gf, smem_u32(Gs), warp * 16);
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  // rows past the sequence end get lse = +inf => p = 0
+  const float L0 = r0 < n ? lse[stat0 + r0] * kLog2e : INFINITY, L1 = r1 < n ? lse[stat0 + r1] * kLog2e : INFINITY;
+  const float D0 = delta_s[warp * 16 + g], D1 = delta_s[warp * 16 + g + 8];
+  const float sl2 = scale * kLog2e;
+  float dq[8][4];
+  zero_acc(dq);
+
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ntiles) {
+      load_tile_async(Ks + (buf ^ 1) * kTileBytes, qkv + d + h * kT, ld, sd, n, (kt + 1) * kT);
+      load_tile_async(Vs + (buf ^ 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, (kt + 1) * kT);
+      load_keep(keep + (buf ^ 1) * kT, key_mask, sd, n, (kt + 1) * kT);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float sacc[8][4], dp[8][4];
+    zero_acc(sacc);
+    zero_acc(dp);
+    warp_gemm<false>(sacc, qf, smem_u32(Ks + buf * kTileBytes));
+    warp_gemm<false>(dp, gf, smem_u32(Vs + buf * kTileBytes));
+    const uint8_t* kp = keep + buf * kT;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
+      const float p00 = k0 ? exp2f(sacc[nt][0] * sl2 - L0) : 0.f, p01 = k1 ? exp2f(sacc[nt][1] * sl2 - L0) : 0.f;
+      const float p10 = k0 ? exp2f(sacc[nt][2] * sl2 - L1) : 0.f, p11 = k1 ? exp2f(sacc[nt][3] * sl2 - L1) : 0.f;
+      sacc[nt][0] = p00 * (dp[nt][0] - D0);
+      sacc[nt][1] = p01 * (dp[nt][1] - D0);
+      sacc[nt][2] = p10 * (dp[nt][2] - D1);
+      sacc[nt][3] = p11 * (dp[nt][3] - D1);
+    }
+    uint32_t dsf[4][4];
+    acc_to_a(dsf, sacc);
+    warp_gemm<true>(dq, dsf, smem_u32(Ks + buf * kTileBytes));
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  store_rows_bf16(dq, scale, scale, Qs, warp * 16, dqkv + h * kT, ld, sd, n, q0);
+}
+
+// ------------------------------------------------------------------------------------------- backward: dk, dv
+// smem: K | V | Q0 | Q1 | dO0 | dO1, lse[2][64], delta[2][64] floats
+constexpr int kDkvSmem = 6 * kTileBytes + 4 * kT * 4;
+
+__global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                                    const int32_t* __restrict__ seq_desc, const uint8_t* __restrict__ key_mask,
+                                                                    const float* __restrict__ lse, const float* __restrict__ delta_ws,
+                                                                    __nv_bfloat16* __restrict__ dqkv, int H, int max_seq_len, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Ks = smem;
+  uint8_t* Vs = smem + kTileBytes;
+  uint8_t* Qs = smem + 2 * kTileBytes;
+  uint8_t* Gs = smem + 4 * kTileBytes;
+  float* lse_s = reinterpret_cast<float*>(smem + 6 * kTileBytes);
+  float* delta_s = lse_s + 2 * kT;
+  const int s = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * kT;
+  const Seq sd = load_seq(seq_desc, s);
+  const int n = sd.len0 + sd.len1;
+  if (k0 >= n) return;
+  const int d = H * kT;
+  const long long ld = 3LL * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ntiles = (n + kT - 1) / kT;
+  const long long stat0 = (static_cast<long long>(s) * H + h) * max_seq_len;
+
+  auto load_stats = [&](int buf, int t0) {
+    if (threadIdx.x < kT) {
+      const int i = t0 + threadIdx.x;
+      lse_s[buf * kT + threadIdx.x] = i < n ? lse[stat0 + i] * kLog2e : INFINITY;  // +inf => p = 0 for absent queries
+      delta_s[buf * kT + threadIdx.x] = i < n ? delta_ws[stat0 + i] : 0.f;
+    }
+  };
+  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, k0);
+  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, k0);
+  load_tile_async(Qs, qkv + h * kT, ld, sd, n, 0);
+  load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, 0);
+  cp_async_commit();
+  load_stats(0, 0);
+
+  // this thread's two key rows
+  const int j0 = k0 + warp * 16 + g, j1 = j0 + 8;
+  const bool keep0 = j0 < n && (key_mask == nullptr || key_mask[seq_row(sd, j0)] != 0);
+  const bool keep1 = j1 < n && (key_mask == nullptr || key_mask[seq_row(sd, j1)] != 0);
+  const float sl2 = scale * kLog2e;
+  uint32_t kf[4][4], vf[4][4];
+  float dk[8][4], dv[8][4];
+  zero_acc(dk);
+  zero_acc(dv);
+
+  for (int qt = 0; qt < ntiles; ++qt) {
+    const int buf = qt & 1;
+    if (qt + 1 < ntiles) {
+      load_tile_async(Qs + (buf ^ 1) * kTileBytes, qkv + h * kT, ld, sd, n, (qt + 1) * kT);
+      load_tile_async(Gs + (buf ^ 1) * kTileBytes, dout + h * kT, static_cast<long long>(d), sd, n, (qt + 1) * kT);
+      load_stats(buf ^ 1, (qt + 1) * kT);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (qt == 0) {
+      load_a_frags(kf, smem_u32(Ks), warp * 16);
+      load_a_frags(vf, smem_u32(Vs), warp * 16);
+    }
+    float st[8][4], dpt[8][4];  // S^T and dP^T: rows = this warp's keys, columns = the tile's queries
+    zero_acc(st);
+    zero_acc(dpt);
+    warp_gemm<false>(st, kf, smem_u32(Qs + buf * kTileBytes));
+    warp_gemm<false>(dpt, vf, smem_u32(Gs + buf * kTileBytes));
+    const float* Lq = lse_s + buf * kT;
+    const float* Dq = delta_s + buf * kT;
+    float ds[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      const float La = Lq[c], Lb = Lq[c + 1], Da = Dq[c], Db = Dq[c + 1];
+      const float p00 = keep0 ? exp2f(st[nt][0] * sl2 - La) : 0.f, p01 = keep0 ? exp2f(st[nt][1] * sl2 - Lb) : 0.f;
+      const float p10 = keep1 ? exp2f(st[nt][2] * sl2 - La) : 0.f, p11 = keep1 ? exp2f(st[nt][3] * sl2 - Lb) : 0.f;
+      ds[nt][0] = p00 * (dpt[nt][0] - Da);
+      ds[nt][1] = p01 * (dpt[nt][1] - Db);
+      ds[nt][2] = p10 * (dpt[nt][2] - Da);
+      ds[nt][3] = p11 * (dpt[nt][3] - Db);
+      st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
+    }
+    uint32_t pf[4][4];
+    acc_to_a(pf, st);
+    warp_gemm<true>(dv, pf, smem_u32(Gs + buf * kTileBytes));
+    acc_to_a(pf, ds);
+    warp_gemm<true>(dk, pf, smem_u32(Qs + buf * kTileBytes));
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  store_rows_bf16(dk, scale, scale, Ks, warp * 16, dqkv + d + h * kT, ld, sd, n, k0);
+  store_rows_bf16(dv, 1.f, 1.f, Vs, warp * 16, dqkv + 2 * d + h * kT, ld, sd, n, k0);
+}
+
+template <typename K>
+int opt_in(K kern, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d): %s", what, bytes, cudaGetErrorString(e));
+    return MOME_ERR_CUDA;
+  }
+  return MOME_OK;
+}
+
+}  // namespace
 
 int attn_fwd_mma(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse, int num_seqs,
                  int max_seq_len, int H, float scale, cudaStream_t stream) {
-  return attn_fwd_simt_dispatch(qkv, MOME_BF16, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, H, scale, stream);
+  static bool configured = false;
+  if (!configured) {
+    int rc = opt_in(attn_fwd_mma_kernel, kFwdSmem, "attn_fwd_mma");
+    if (rc != MOME_OK) return rc;
+    configured = true;
+  }
+  dim3 grid((max_seq_len + kT - 1) / kT, H, num_seqs);
+  attn_fwd_mma_kernel<<<grid, kThreads, kFwdSmem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), seq_desc, key_mask,
+                                                            static_cast<__nv_bfloat16*>(out), lse, H, max_seq_len, scale);
+  return check_launch("attn_fwd_mma");
 }
+
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask,
                  const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len, int H, float scale,
                  cudaStream_t stream) {
-  return attn_bwd_simt_dispatch(qkv, out, dout, MOME_BF16, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, H, scale, stream);
+  static bool configured = false;
+  if (!configured) {
+    int rc = opt_in(attn_bwd_dq_mma_kernel, kDqSmem, "attn_bwd_dq_mma");
+    if (rc != MOME_OK) return rc;
+    rc = opt_in(attn_bwd_dkv_mma_kernel, kDkvSmem, "attn_bwd_dkv_mma");
+    if (rc != MOME_OK) return rc;
+    configured = true;
+  }
+  dim3 grid((max_seq_len + kT - 1) / kT, H, num_seqs);
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(dout);
+  __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+  attn_bwd_dq_mma_kernel<<<grid, kThreads, kDqSmem, stream>>>(q, static_cast<const __nv_bfloat16*>(out), go, seq_desc, key_mask, lse, dq,
+                                                              delta_ws, H, max_seq_len, scale);
+  int rc = check_launch("attn_bwd_dq_mma");
+  if (rc != MOME_OK) return rc;
+  attn_bwd_dkv_mma_kernel<<<grid, kThreads, kDkvSmem, stream>>>(q, go, seq_desc, key_mask, lse, delta_ws, dq, H, max_seq_len, scale);
+  return check_launch("attn_bwd_dkv_mma");
 }
+
 }  // namespace mome

@@ -283,7 +283,8 @@ class VLMO(nn.Module):
 
     # ---- embeddings (reference vlmo.py:298-324)
     def embed_img(self, x, img_masks, bool_masked_pos=None, img_token_type_idx=1):
-        with self._autocast():
+        # fp32 validation path: keep cuDNN off TF32 so that the patch projection is true fp32
+        with self._autocast(), torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision == 'bf16'):
             x = self.patch_embed(x)
         x = x.float()
         B, P, _ = x.shape
