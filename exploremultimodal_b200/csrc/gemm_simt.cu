@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
       if (g.bias) v += g.bias[n];
       switch (p.epilogue) {
         case MOME_EPI_GELU:
-          g.out2[m * p.ldo2 + n] = v;
+          g.out2[m * p.ldo2 + n] = gelu_erf_grad(v);
           g.out[m * p.ldo + n] = gelu_erf(v);
           break;
         case MOME_EPI_RESIDUAL:
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
           g.out[m * p.ldo + n] = g.res[m * p.ldres + n] + (p.gamma ? p.gamma[n] : 1.f) * v;
           break;
         case MOME_EPI_DGELU:
-          g.out[m * p.ldo + n] = v * gelu_erf_grad(g.aux[m * p.ldaux + n]);
+          g.out[m * p.ldo + n] = v * g.aux[m * p.ldaux + n];
           break;
         default:
           g.out[m * p.ldo + n] = v;

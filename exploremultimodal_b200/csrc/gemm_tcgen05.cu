@@ -1,17 +1,24 @@
-// K2: persistent, warp-specialised grouped GEMM on the 5th-gen tensor cores.
+// K2: persistent, warp-specialised grouped GEMM on the 5th-gen tensor cores, CTA pairs.
 //
 //   out[m, n] = epilogue( sum_k A(m, k) * B(n, k) )   per group (expert segment of the packed tokens)
 //
-// One CTA per SM, 256 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
-// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused epilogue ->
-// global). Operands are staged by TMA into a 4/6-deep ring of SWIZZLE_128B shared-memory tiles;
-// accumulators (128 x BLOCK_N fp32) live in TMEM, double-buffered so that the epilogue of work item
-// i overlaps the MMAs of item i+1. Both operands may be K-major or MN-major (transpose bits of the
-// instruction descriptor), which is how forward, dgrad and wgrad all run on this one kernel without
-// materialising transposed copies (see include/mome.h). wgrad uses split-K with fp32 red.add.
+// Launch: 148 CTAs as 74 two-CTA clusters (one pair per TPC), 384 threads per CTA:
+//   warp 0      TMA producer (one elected lane): its CTA's 128 rows of A and its half of B per k-block
+//   warp 1      tcgen05.mma issuer (one elected lane of the LEADER CTA): cta_group::2, M = 256, N = BLOCK_N
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: TMEM -> registers -> per-warp padded smem tile (transpose) -> fused epilogue with
+//               128-bit row-contiguous global loads / stores
+// A work item is a 256 x BLOCK_N output tile (x one k-split): each CTA of the pair owns 128 accumulator
+// lanes (rows) x BLOCK_N columns in TMEM, double-buffered so the epilogue of item i overlaps the MMAs
+// of item i+1. Pairing halves the shared-memory / L2 traffic per FLOP for B: at 128 x 256 single-CTA
+// tiles the kernel was L2-bandwidth bound (profiles/r01_launches_v1_summary.md).
+// Operands are staged by TMA into a ring of SWIZZLE_128B tiles; both may be K-major or MN-major
+// (transpose bits of the instruction descriptor), so forward, dgrad and wgrad all run on this kernel
+// without transposed copies (include/mome.h). wgrad uses split-K with fp32 red.add.
 //
 // Replaces: F.linear / timm Mlp / residual adds of the reference Block (vlmo.py:76-78, 96, 190-196).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -22,11 +29,21 @@
 
 namespace mome {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+namespace v1 {
+int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream);
+}
+
+namespace {
+
+constexpr int PAIR_M = 256;   // rows of a work item (two CTAs x 128)
+constexpr int CTA_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int kAtomBytes = BLOCK_K * 128;  // one 64x64 MN-major box / 64 rows of a K-major tile
+constexpr int kStagePitch = 36;            // floats per row of the per-warp transpose tile (32 + pad, 16 B aligned)
+constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
 
 struct GemmGroupDev {
   void* out;
@@ -72,109 +89,85 @@ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
   return w;
 }
 
-// Fused epilogue for 32 consecutive columns of one output row.
-__device__ __forceinline__ void epilogue_row32(const GemmParams& p, const GemmGroupDev& g, float (&v)[32], long long row,
-                                               int col0) {
-  if (p.epilogue == MOME_EPI_ATOMIC) {
-    float* o = reinterpret_cast<float*>(g.out) + row * p.ldo + col0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(o + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+__device__ __forceinline__ uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
+__device__ __forceinline__ float4 unpack4_bf16(uint2 u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Operand a fused epilogue reads from global memory besides the accumulator (4 columns of one row):
+// the fp32 residual (RESIDUAL) or the stashed bf16 gelu'(z) (DGELU). Loaded a chunk ahead of its use.
+template <int EPI>
+struct EpiExtra {
+  float4 v;
+  __device__ __forceinline__ void load(const GemmParams& p, const GemmGroupDev& g, long long row, int col) {
+    if (EPI == MOME_EPI_RESIDUAL) {
+      v = *reinterpret_cast<const float4*>(g.res + row * p.ldres + col);
+    } else if (EPI == MOME_EPI_DGELU) {
+      v = unpack4_bf16(*reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.aux) + row * p.ldaux + col));
+    }
+  }
+};
+
+// Fused epilogue for 4 consecutive columns [col, col+4) of one output row. `b4` / `gm4` are the bias and
+// LayerScale values of those columns (hoisted by the caller), `ex` the prefetched residual / gelu'.
+template <int EPI>
+__device__ __forceinline__ void epilogue4(const GemmParams& p, const GemmGroupDev& g, float4 v, long long row, int col, float4 b4,
+                                          float4 gm4, float4 ex) {
+  if (EPI == MOME_EPI_ATOMIC) {
+    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col), v);
     return;
   }
-  if (g.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = __ldg(b4 + i);
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  }
-  if (p.epilogue == MOME_EPI_GELU) {
-    // z is rounded to bf16 first (what an autocast Linear hands to GELU); both z and gelu(z) are kept
-    uint4* z4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col0);
-    uint4* u4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t zp[4], up[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float z0 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j]));
-        const float z1 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j + 1]));
-        zp[j] = pack_bf16(z0, z1);
-        up[j] = pack_bf16(gelu_erf(z0), gelu_erf(z1));
-      }
-      z4[i] = make_uint4(zp[0], zp[1], zp[2], zp[3]);
-      u4[i] = make_uint4(up[0], up[1], up[2], up[3]);
-    }
+  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+  if (EPI == MOME_EPI_GELU) {
+    // z is rounded to bf16 first (what an autocast Linear hands to GELU); out = gelu(z), out2 = gelu'(z)
+    float4 u, du;
+    gelu_fast(bf16_round(v.x), u.x, du.x);
+    gelu_fast(bf16_round(v.y), u.y, du.y);
+    gelu_fast(bf16_round(v.z), u.z, du.z);
+    gelu_fast(bf16_round(v.w), u.w, du.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(u);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col) = pack4_bf16(du);
     return;
   }
-  if (p.epilogue == MOME_EPI_RESIDUAL) {
-    // b = bf16(acc + bias) is what the reference's autocast Linear returns; residual stream stays fp32
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-    if (g.out2 != nullptr) {
-      uint4* b4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        b4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                           pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-    }
-    const float4* r4 = reinterpret_cast<const float4*>(g.res + row * p.ldres + col0);
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 r = r4[i];
-      float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.gamma != nullptr) gm = __ldg(reinterpret_cast<const float4*>(p.gamma + col0) + i);
-      r.x += gm.x * v[4 * i]; r.y += gm.y * v[4 * i + 1]; r.z += gm.z * v[4 * i + 2]; r.w += gm.w * v[4 * i + 3];
-      o4[i] = r;
-    }
+  if (EPI == MOME_EPI_RESIDUAL) {
+    // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
+    v = make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
+    if (g.out2 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col) = pack4_bf16(v);
+    float4 r = ex;
+    r.x = fmaf(gm4.x, v.x, r.x); r.y = fmaf(gm4.y, v.y, r.y); r.z = fmaf(gm4.z, v.z, r.z); r.w = fmaf(gm4.w, v.w, r.w);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = r;
     return;
   }
-  if (p.epilogue == MOME_EPI_DGELU) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.aux) + row * p.ldaux + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 a = a4[i];
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 z = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-        v[8 * i + 2 * j] *= gelu_erf_grad(__low2float(z));
-        v[8 * i + 2 * j + 1] *= gelu_erf_grad(__high2float(z));
-      }
-    }
+  if (EPI == MOME_EPI_DGELU) {
+    v.x *= ex.x; v.y *= ex.y; v.z *= ex.z; v.w *= ex.w;
   }
-  // STORE (and the tail of DGELU)
-  if (p.out_bf16) {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                         pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-  } else {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
+  if (p.out_bf16)
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(v);
+  else
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = v;
 }
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int A_BYTES = CTA_M * 128;            // this CTA's 128 rows x 64 k
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 128;    // this CTA's half of the N tile x 64 k
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 5 : 7;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int EPI_BYTES = kEpiWarps * kStageBytesPerWarp;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -182,6 +175,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.num_groups; ++g) {
@@ -191,58 +186,60 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // leader's copy is the one in use: one arrive.expect_tx + both CTAs' TMA bytes
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tfull_bar[s], 1);                // multicast tcgen05.commit
+      mbar_init(&tempty_bar[s], 2 * kEpiWarps);   // leader's copy: every epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible before any remote arrive / MMA
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = pair; item < p.total_items; item += num_pairs) {
         const WorkItem w = decode_item(p, item);
+        const int m0 = w.m_tile * PAIR_M + cta_rank * CTA_M;
+        const int n0 = w.n_tile * BLOCK_N + cta_rank * (BLOCK_N / 2);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           if (!A_MN) {
-            tma_load_2d(a_dst, &p.tma_a[w.g], &full_bar[stage], kb * BLOCK_K, w.m_tile * BLOCK_M);
+            tma_load_2d_pair(a_dst, &p.tma_a[w.g], &full_bar[stage], kb * BLOCK_K, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(a_dst + j * kAtomBytes, &p.tma_a[w.g], &full_bar[stage], w.m_tile * BLOCK_M + j * 64, kb * BLOCK_K);
+            for (int j = 0; j < CTA_M / 64; ++j)
+              tma_load_2d_pair(a_dst + j * kAtomBytes, &p.tma_a[w.g], &full_bar[stage], m0 + j * 64, kb * BLOCK_K);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &p.tma_b[w.g], &full_bar[stage], kb * BLOCK_K, w.n_tile * BLOCK_N);
+            tma_load_2d_pair(b_dst, &p.tma_b[w.g], &full_bar[stage], kb * BLOCK_K, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(b_dst + j * kAtomBytes, &p.tma_b[w.g], &full_bar[stage], w.n_tile * BLOCK_N + j * 64, kb * BLOCK_K);
+            for (int j = 0; j < BLOCK_N / 128; ++j)
+              tma_load_2d_pair(b_dst + j * kAtomBytes, &p.tma_b[w.g], &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (cta_rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, BLOCK_N, A_MN, B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = pair; item < p.total_items; item += num_pairs) {
         const WorkItem w = decode_item(p, item);
         if (w.kb0 >= w.kb1) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -259,50 +256,90 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                                          : umma_smem_desc(a_base + k * (UMMA_K * 2), 0, 1024);
             const uint64_t b_desc = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), kAtomBytes, 1024)
                                          : umma_smem_desc(b_base + k * (UMMA_K * 2), 0, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit_pair(&tfull_bar[acc]);  // accumulator complete -> epilogue warps of both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int ew = warp - 4;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which half of the tile's columns
+    float* stage_w = epi_stage + ew * (kStageBytesPerWarp / 4);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = pair; item < p.total_items; item += num_pairs) {
       const WorkItem w = decode_item(p, item);
       if (w.kb0 >= w.kb1) continue;
       const GemmGroupDev& g = p.g[w.g];
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const long long row = static_cast<long long>(w.m_tile) * BLOCK_M + ew * 32 + lane;
-      const bool row_ok = row < g.M;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = w.n_tile * BLOCK_N + c * 32;
-        if (row_ok && col0 < p.N) {
-          float v[32];
+      const long long row0 = static_cast<long long>(w.m_tile) * PAIR_M + cta_rank * CTA_M + quarter * 32;
+      constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
+      constexpr bool kHasExtra = EPI == MOME_EPI_RESIDUAL || EPI == MOME_EPI_DGELU;
+      const int col_base = w.n_tile * BLOCK_N + half * (BLOCK_N / 2) + c4;
+      // residual / gelu' operands of chunk 0 (the later chunks are fetched one chunk ahead, below)
+      EpiExtra<EPI> nxt[8];
+      if (kHasExtra && col_base < p.N) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_row32(p, g, v, row, col0);
-        }
+        for (int it = 0; it < 8; ++it)
+          if (row0 + it * 4 + rsub < g.M) nxt[it].load(p, g, row0 + it * 4 + rsub, col_base);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int tcol = half * (BLOCK_N / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + tcol, r);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // all of this warp's accumulator reads are done: hand the TMEM stage back to the MMA issuer
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+        float* mine = stage_w + lane * kStagePitch;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        __syncwarp();
+        const int col = col_base + c * 32;
+        float4 cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = nxt[it].v;
+        if (kHasExtra && c + 1 < kChunks && col + 32 < p.N) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (row0 + it * 4 + rsub < g.M) nxt[it].load(p, g, row0 + it * 4 + rsub, col + 32);
+        }
+        if (col < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (EPI != MOME_EPI_ATOMIC && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+          if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const long long row = row0 + rr;
+            if (row < g.M) {
+              const float4 v = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + c4);
+              epilogue4<EPI>(p, g, v, row, col, b4, gm4, cur[it]);
+            }
+          }
+        }
+        __syncwarp();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer can still touch its barriers / TMEM
+  if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -310,7 +347,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -324,8 +361,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [outer][inner] with row pitch ld (elements), 128B-swizzled box {box_inner, box_outer}.
-static int encode_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                          int box_outer) {
+int encode_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -355,15 +391,15 @@ struct ProfRec {
   cudaEvent_t a, b;
   double flops;
 };
-static std::mutex g_prof_mu;
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_pair_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -372,67 +408,63 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
     }
     configured = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
-  return check_launch("gemm_tcgen05");
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  return check_launch("gemm_pair");
 }
+
+// The epilogue is a template parameter; only the (major, epilogue) pairs the block uses are instantiated.
+template <int BLOCK_N>
+int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_t stream) {
+  if (!a_mn && !b_mn) {
+    switch (p.epilogue) {
+      case MOME_EPI_STORE: return launch_one<BLOCK_N, false, false, MOME_EPI_STORE>(p, grid, stream);
+      case MOME_EPI_GELU: return launch_one<BLOCK_N, false, false, MOME_EPI_GELU>(p, grid, stream);
+      case MOME_EPI_RESIDUAL: return launch_one<BLOCK_N, false, false, MOME_EPI_RESIDUAL>(p, grid, stream);
+      case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, false, false, MOME_EPI_ATOMIC>(p, grid, stream);
+    }
+  } else if (!a_mn && b_mn) {
+    switch (p.epilogue) {
+      case MOME_EPI_STORE: return launch_one<BLOCK_N, false, true, MOME_EPI_STORE>(p, grid, stream);
+      case MOME_EPI_DGELU: return launch_one<BLOCK_N, false, true, MOME_EPI_DGELU>(p, grid, stream);
+      case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, false, true, MOME_EPI_ATOMIC>(p, grid, stream);
+    }
+  } else if (a_mn && b_mn) {
+    switch (p.epilogue) {
+      case MOME_EPI_STORE: return launch_one<BLOCK_N, true, true, MOME_EPI_STORE>(p, grid, stream);
+      case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, true, true, MOME_EPI_ATOMIC>(p, grid, stream);
+    }
+  }
+  set_error("gemm(bf16): operand majors (%d, %d) with epilogue %d are not instantiated", (int)a_mn, (int)b_mn, p.epilogue);
+  return MOME_ERR_UNSUPPORTED;
+}
+
+bool use_v1() {
+  static const bool v = [] {
+    const char* e = getenv("MOME_GEMM_V1");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
+}  // namespace
 
 int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
   MOME_REQUIRE(a->num_groups >= 1 && a->num_groups <= MOME_MAX_GROUPS, "gemm: num_groups %d", a->num_groups);
   MOME_REQUIRE(a->N > 0 && a->N % 32 == 0, "gemm(bf16): N=%lld must be a positive multiple of 32", (long long)a->N);
   const bool a_mn = a->a_major == 1, b_mn = a->b_major == 1;
   MOME_REQUIRE(!(a_mn && !b_mn), "gemm(bf16): A MN-major with B K-major is not instantiated");
-  const int block_n = (a->N % 256 == 0) ? 256 : 128;
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.num_groups = a->num_groups;
-  p.N = static_cast<int>(a->N);
-  p.n_tiles = static_cast<int>((a->N + block_n - 1) / block_n);
-  p.epilogue = a->epilogue;
-  p.out_bf16 = a->out_dtype == MOME_BF16;
-  p.ldo = a->ldo; p.ldo2 = a->ldo2; p.ldres = a->ldres; p.ldaux = a->ldaux;
-  p.gamma = a->gamma;
   MOME_REQUIRE(a->epilogue != MOME_EPI_ATOMIC || a->out_dtype == MOME_F32, "gemm: ATOMIC epilogue needs fp32 out");
   MOME_REQUIRE(a->epilogue != MOME_EPI_RESIDUAL || a->out_dtype == MOME_F32, "gemm: RESIDUAL epilogue needs fp32 out");
   MOME_REQUIRE((a->epilogue != MOME_EPI_GELU && a->epilogue != MOME_EPI_DGELU) || a->out_dtype == MOME_BF16,
                "gemm(bf16): GELU/DGELU epilogues write bf16");
   MOME_REQUIRE(a->ldo % 8 == 0 && a->ldo2 % 8 == 0 && a->ldres % 4 == 0 && a->ldaux % 8 == 0, "gemm: leading dims must keep rows 16-byte aligned");
 
-  long long tiles = 0, max_kb = 0;
   double flops = 0;
   for (int g = 0; g < a->num_groups; ++g) {
     const MomeGemmGroup& s = a->group[g];
     MOME_REQUIRE(s.M > 0 && s.K > 0, "gemm: group %d has M=%lld K=%lld (drop empty groups on the host)", g, (long long)s.M, (long long)s.K);
-    tiles += ((s.M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles;
-    max_kb = std::max<long long>(max_kb, (s.K + BLOCK_K - 1) / BLOCK_K);
     flops += 2.0 * double(s.M) * double(a->N) * double(s.K);
   }
-  int splits = 1;
-  if (a->epilogue == MOME_EPI_ATOMIC) {
-    splits = a->split_k > 0 ? a->split_k : static_cast<int>((2 * sm_count() + tiles - 1) / tiles);
-    splits = std::max(1, std::min<int>(splits, static_cast<int>(std::max<long long>(1, max_kb / 4))));
-  }
-  p.splits = splits;
-  int item = 0;
-  for (int g = 0; g < a->num_groups; ++g) {
-    const MomeGemmGroup& s = a->group[g];
-    GemmGroupDev& d = p.g[g];
-    d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux;
-    d.M = static_cast<int>(s.M);
-    d.k_blocks = static_cast<int>((s.K + BLOCK_K - 1) / BLOCK_K);
-    d.item_start = item;
-    item += static_cast<int>((s.M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles * splits;
-    int rc;
-    // K-major operand: tensor [rows][K], box {64 (K), tile rows}; MN-major: tensor [K][rows], box {64 (MN), 64 (K)}
-    rc = a_mn ? encode_bf16_2d(&p.tma_a[g], s.a, s.M, s.K, a->lda, 64, BLOCK_K)
-              : encode_bf16_2d(&p.tma_a[g], s.a, s.K, s.M, a->lda, BLOCK_K, BLOCK_M);
-    if (rc != MOME_OK) return rc;
-    rc = b_mn ? encode_bf16_2d(&p.tma_b[g], s.b, a->N, s.K, a->ldb, 64, BLOCK_K)
-              : encode_bf16_2d(&p.tma_b[g], s.b, s.K, a->N, a->ldb, BLOCK_K, block_n);
-    if (rc != MOME_OK) return rc;
-  }
-  p.total_items = item;
-  const int grid = std::min(item, sm_count());
-
   ProfRec rec{};
   bool prof = false;
   {
@@ -446,12 +478,67 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     cudaEventRecord(rec.a, stream);
   }
   int rc;
-  if (block_n == 256) {
-    rc = a_mn ? launch_gemm<256, true, true>(p, grid, stream)
-              : (b_mn ? launch_gemm<256, false, true>(p, grid, stream) : launch_gemm<256, false, false>(p, grid, stream));
+  if (use_v1()) {
+    rc = v1::gemm_bf16(a, stream);
   } else {
-    rc = a_mn ? launch_gemm<128, true, true>(p, grid, stream)
-              : (b_mn ? launch_gemm<128, false, true>(p, grid, stream) : launch_gemm<128, false, false>(p, grid, stream));
+    const int block_n = (a->N % 256 == 0) ? 256 : 128;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_groups = a->num_groups;
+    p.N = static_cast<int>(a->N);
+    p.n_tiles = static_cast<int>((a->N + block_n - 1) / block_n);
+    p.epilogue = a->epilogue;
+    p.out_bf16 = a->out_dtype == MOME_BF16;
+    p.ldo = a->ldo; p.ldo2 = a->ldo2; p.ldres = a->ldres; p.ldaux = a->ldaux;
+    p.gamma = a->gamma;
+    const int pairs = std::max(1, sm_count() / 2);
+    long long tiles = 0, max_kb = 0;
+    for (int g = 0; g < a->num_groups; ++g) {
+      const MomeGemmGroup& s = a->group[g];
+      tiles += ((s.M + PAIR_M - 1) / PAIR_M) * p.n_tiles;
+      max_kb = std::max<long long>(max_kb, (s.K + BLOCK_K - 1) / BLOCK_K);
+    }
+    int splits = 1;
+    if (a->epilogue == MOME_EPI_ATOMIC) {
+      if (a->split_k > 0) {
+        splits = a->split_k;
+      } else {
+        // fewest k-splits that fill the machine for >= 2 waves with <= 10 % tail loss (else the best seen)
+        const int max_splits = static_cast<int>(std::max<long long>(1, max_kb / 4));
+        double best_eff = -1.0;
+        for (int s = 1; s <= std::min(max_splits, 64); ++s) {
+          const long long items = tiles * s;
+          const long long waves = (items + pairs - 1) / pairs;
+          const double eff = double(items) / double(waves * pairs);
+          if (eff > best_eff + 1e-9) { best_eff = eff; splits = s; }
+          if (waves >= 2 && eff >= 0.9) { splits = s; break; }
+        }
+      }
+      splits = std::max(1, std::min<int>(splits, static_cast<int>(std::max<long long>(1, max_kb))));
+    }
+    p.splits = splits;
+    int item = 0;
+    rc = MOME_OK;
+    for (int g = 0; g < a->num_groups && rc == MOME_OK; ++g) {
+      const MomeGemmGroup& s = a->group[g];
+      GemmGroupDev& d = p.g[g];
+      d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux;
+      d.M = static_cast<int>(s.M);
+      d.k_blocks = static_cast<int>((s.K + BLOCK_K - 1) / BLOCK_K);
+      d.item_start = item;
+      item += static_cast<int>((s.M + PAIR_M - 1) / PAIR_M) * p.n_tiles * splits;
+      // K-major operand: tensor [rows][K], box {64 (K), rows per CTA}; MN-major: tensor [K][rows], box {64 (MN), 64 (K)}
+      rc = a_mn ? encode_bf16_2d(&p.tma_a[g], s.a, s.M, s.K, a->lda, 64, BLOCK_K)
+                : encode_bf16_2d(&p.tma_a[g], s.a, s.K, s.M, a->lda, BLOCK_K, CTA_M);
+      if (rc != MOME_OK) break;
+      rc = b_mn ? encode_bf16_2d(&p.tma_b[g], s.b, a->N, s.K, a->ldb, 64, BLOCK_K)
+                : encode_bf16_2d(&p.tma_b[g], s.b, s.K, a->N, a->ldb, BLOCK_K, block_n / 2);
+    }
+    if (rc == MOME_OK) {
+      p.total_items = item;
+      const int grid = 2 * std::min(item, pairs);
+      rc = block_n == 256 ? launch_gemm<256>(p, a_mn, b_mn, grid, stream) : launch_gemm<128>(p, a_mn, b_mn, grid, stream);
+    }
   }
   if (prof) {
     cudaEventRecord(rec.b, stream);

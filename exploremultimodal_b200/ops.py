@@ -234,7 +234,7 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
         g_wgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=u.data_ptr() + s * hid * es, M=d, K=n, out=dw2.data_ptr()))
         g_wgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=h2.data_ptr() + s * d * es, M=hid, K=n, out=dw1.data_ptr()))
         g_dgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=w1.data_ptr(), M=n, K=hid, out=dh2.data_ptr() + s * d * es))
-    # dz = (dbr2 @ W2) * gelu'(z)
+    # dz = (dbr2 @ W2) * gelu'(z); `z` holds gelu'(z), stashed by the forward GELU epilogue
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_DGELU, code, hid, d, hid, hid, g_dgrad2, ldaux=hid)
     # dW2 += dbr2^T @ u
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, hid, d, hid, hid, g_wgrad2)

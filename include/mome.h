@@ -66,9 +66,9 @@ int mome_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
  * fused rows -> 'vl'): same N/K/epilogue, per-group pointers and row counts. */
 enum MomeEpilogue {
   MOME_EPI_STORE = 0,    /* out = acc + bias                                   (qkv, dgrad) */
-  MOME_EPI_GELU = 1,     /* out2 = z = acc + bias (pre-activation), out = gelu_erf(z)   (fc1) */
+  MOME_EPI_GELU = 1,     /* z = acc + bias; out = gelu_erf(z), out2 = gelu_erf'(z)      (fc1) */
   MOME_EPI_RESIDUAL = 2, /* out2 = b = acc + bias; out(fp32) = res + gamma * b  (proj, fc2) */
-  MOME_EPI_DGELU = 3,    /* out = acc * gelu_erf'(aux)                     (fc2 dgrad -> dz) */
+  MOME_EPI_DGELU = 3,    /* out = acc * aux, aux = the saved gelu_erf'(z)  (fc2 dgrad -> dz) */
   MOME_EPI_ATOMIC = 4    /* out(fp32) += acc via red.add (split-K wgrad)                     */
 };
 
