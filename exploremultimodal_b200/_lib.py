@@ -15,13 +15,13 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 K_MAJOR, MN_MAJOR = 0, 1
 MAX_GROUPS = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class GemmGroup(C.Structure):
     _fields_ = [('a', C.c_void_p), ('b', C.c_void_p), ('M', C.c_int64), ('K', C.c_int64),
                 ('out', C.c_void_p), ('out2', C.c_void_p), ('bias', C.c_void_p), ('res', C.c_void_p),
-                ('aux', C.c_void_p)]
+                ('aux', C.c_void_p), ('colsum', C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -40,6 +40,7 @@ _SIGNATURES = {
     'mome_sm_count': (C.c_int, []),
     'mome_ln_fwd': (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _L, _L, _F, _P]),
     'mome_ln_bwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
+    'mome_ln_bwd_scale': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
     'mome_scale_bwd': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _L, _L, _P]),
     'mome_colsum': (C.c_int, [_P, C.c_int, _L, _L, _L, _P, _P]),
     'mome_cast_bf16': (C.c_int, [_P, _P, _L, _P]),

@@ -16,6 +16,7 @@ struct SimtGroup {
   const float* bias;
   const float* res;
   const float* aux;
+  float* colsum;
   int M, K;
 };
 struct SimtParams {
@@ -82,10 +83,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
           g.out[m * p.ldo + n] = g.res[m * p.ldres + n] + (p.gamma ? p.gamma[n] : 1.f) * v;
           break;
         case MOME_EPI_DGELU:
-          g.out[m * p.ldo + n] = v * g.aux[m * p.ldaux + n];
+          v *= g.aux[m * p.ldaux + n];
+          g.out[m * p.ldo + n] = v;
+          if (g.colsum) atomicAdd(g.colsum + n, v);
           break;
         default:
           g.out[m * p.ldo + n] = v;
+          if (g.colsum) atomicAdd(g.colsum + n, v);
       }
     }
   }
@@ -101,7 +105,7 @@ static int gemm_f32(const MomeGemmArgs* a, cudaStream_t stream) {
     const MomeGemmGroup& s = a->group[g];
     MOME_REQUIRE(s.M > 0 && s.K > 0, "gemm: group %d has M=%lld K=%lld", g, (long long)s.M, (long long)s.K);
     p.g[g] = SimtGroup{static_cast<const float*>(s.a), static_cast<const float*>(s.b), static_cast<float*>(s.out),
-                       static_cast<float*>(s.out2), s.bias, s.res, static_cast<const float*>(s.aux), (int)s.M, (int)s.K};
+                       static_cast<float*>(s.out2), s.bias, s.res, static_cast<const float*>(s.aux), s.colsum, (int)s.M, (int)s.K};
     max_m = std::max<long long>(max_m, s.M);
   }
   p.gamma = a->gamma;

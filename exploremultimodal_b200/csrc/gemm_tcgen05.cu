@@ -51,6 +51,7 @@ struct GemmGroupDev {
   const float* bias;
   const float* res;
   const void* aux;
+  float* colsum;
   int M;
   int k_blocks;
   int item_start;
@@ -114,11 +115,11 @@ struct EpiExtra {
 // Fused epilogue for 4 consecutive columns [col, col+4) of one output row. `b4` / `gm4` are the bias and
 // LayerScale values of those columns (hoisted by the caller), `ex` the prefetched residual / gelu'.
 template <int EPI>
-__device__ __forceinline__ void epilogue4(const GemmParams& p, const GemmGroupDev& g, float4 v, long long row, int col, float4 b4,
-                                          float4 gm4, float4 ex) {
+__device__ __forceinline__ float4 epilogue4(const GemmParams& p, const GemmGroupDev& g, float4 v, long long row, int col, float4 b4,
+                                            float4 gm4, float4 ex) {
   if (EPI == MOME_EPI_ATOMIC) {
     atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col), v);
-    return;
+    return v;
   }
   v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
   if (EPI == MOME_EPI_GELU) {
@@ -130,7 +131,7 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, const GemmGroupDe
     gelu_fast(bf16_round(v.w), u.w, du.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(u);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col) = pack4_bf16(du);
-    return;
+    return u;
   }
   if (EPI == MOME_EPI_RESIDUAL) {
     // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
@@ -139,15 +140,18 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, const GemmGroupDe
     float4 r = ex;
     r.x = fmaf(gm4.x, v.x, r.x); r.y = fmaf(gm4.y, v.y, r.y); r.z = fmaf(gm4.z, v.z, r.z); r.w = fmaf(gm4.w, v.w, r.w);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = r;
-    return;
+    return r;
   }
   if (EPI == MOME_EPI_DGELU) {
     v.x *= ex.x; v.y *= ex.y; v.z *= ex.z; v.w *= ex.w;
   }
-  if (p.out_bf16)
+  if (p.out_bf16) {
+    v = make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(v);
-  else
+  } else {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = v;
+  }
+  return v;
 }
 
 template <int BLOCK_N>
@@ -322,13 +326,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (EPI != MOME_EPI_ATOMIC && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
           if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
             const long long row = row0 + rr;
             if (row < g.M) {
               const float4 v = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + c4);
-              epilogue4<EPI>(p, g, v, row, col, b4, gm4, cur[it]);
+              const float4 o = epilogue4<EPI>(p, g, v, row, col, b4, gm4, cur[it]);
+              cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+            }
+          }
+          if ((EPI == MOME_EPI_STORE || EPI == MOME_EPI_DGELU) && g.colsum != nullptr) {
+            // fused bias gradient: sum the stored values over this warp's 32 rows, one red.add per column
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (rsub == 0) {
+              atomicAdd(g.colsum + col, cs.x); atomicAdd(g.colsum + col + 1, cs.y);
+              atomicAdd(g.colsum + col + 2, cs.z); atomicAdd(g.colsum + col + 3, cs.w);
             }
           }
         }
@@ -480,6 +498,9 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
   int rc;
   if (use_v1()) {
     rc = v1::gemm_bf16(a, stream);
+    for (int g = 0; g < a->num_groups && rc == MOME_OK; ++g)
+      if (a->group[g].colsum != nullptr)
+        rc = mome_colsum(a->group[g].out, a->out_dtype, a->group[g].M, a->N, a->ldo, a->group[g].colsum, stream);
   } else {
     const int block_n = (a->N % 256 == 0) ? 256 : 128;
     GemmParams p;
@@ -522,7 +543,7 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     for (int g = 0; g < a->num_groups && rc == MOME_OK; ++g) {
       const MomeGemmGroup& s = a->group[g];
       GemmGroupDev& d = p.g[g];
-      d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux;
+      d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux; d.colsum = s.colsum;
       d.M = static_cast<int>(s.M);
       d.k_blocks = static_cast<int>((s.K + BLOCK_K - 1) / BLOCK_K);
       d.item_start = item;

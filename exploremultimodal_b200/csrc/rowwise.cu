@@ -70,151 +70,173 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const float* __rest
   }
 }
 
-// Flush per-lane column partials: combine the 8 warps of the CTA in smem, one red.add per column.
-template <int NACC, int NV>
-__device__ __forceinline__ void flush_columns(float4 (&acc)[NACC][NV], float* const (&dst)[NACC], int nvec,
-                                              float* smem /* [8][d] */, int d) {
+// ------------------------------------------------------------------------------------------- column-owner kernels
+// Backward row kernels need per-column reductions over all rows (dweight, dbias, dgamma). Here a thread
+// owns 4 consecutive columns for every row its CTA visits, so those reductions are 4 registers per
+// output and one red.add per column per CTA at the end; row statistics (LayerNorm backward needs two
+// sums over the row) are a block reduction batched over R rows per iteration. Few registers -> several
+// CTAs per SM and R x 3 independent 128-bit loads in flight per thread, which is what an HBM-bound
+// kernel needs.
+constexpr int kColRows = 4;  // rows per iteration
+
+template <int NVAL>
+__device__ __forceinline__ void block_sums(float (&v)[NVAL], float* red /* [nwarps][NVAL] */, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int a = 0; a < NACC; ++a) {
-    if (dst[a] == nullptr) continue;
-    __syncthreads();
+  for (int k = 0; k < NVAL; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 32 + lane;
-      if (c < nvec) *reinterpret_cast<float4*>(smem + warp * d + 4 * c) = acc[a][i];
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < d; j += kRowThreads) {
-      float s = 0.f;
+    for (int k = 0; k < NVAL; ++k) red[warp * NVAL + k] = v[k];
+  }
+  __syncthreads();
 #pragma unroll
-      for (int wv = 0; wv < kRowThreads / 32; ++wv) s += smem[wv * d + j];
-      atomicAdd(dst[a] + j, s);
-    }
+  for (int k = 0; k < NVAL; ++k) v[k] = 0.f;
+  for (int w = 0; w < nwarps; ++w) {
+#pragma unroll
+    for (int k = 0; k < NVAL; ++k) v[k] += red[w * NVAL + k];
   }
 }
 
-// ------------------------------------------------------------------------------------------- LN bwd
-template <typename InT, int NV>
-__global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
-                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             const float* __restrict__ w, const float* dres,
-                                                             float* dx, float* dw, float* db, long long rows,
-                                                             int d) {
-  extern __shared__ float smem_cols[];
-  const int lane = threadIdx.x & 31;
-  const int nvec = d >> 2;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * kRowThreads + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * kRowThreads) >> 5;
-  float4 acc[2][NV];
+__device__ __forceinline__ void red_add4(float* dst, float4 v) {
+  atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+}
+__device__ __forceinline__ float4 bf16_round4(float4 v) {
+  return make_float4(__bfloat162float(__float2bfloat16_rn(v.x)), __bfloat162float(__float2bfloat16_rn(v.y)),
+                     __bfloat162float(__float2bfloat16_rn(v.z)), __bfloat162float(__float2bfloat16_rn(v.w)));
+}
+
+// LayerNorm backward (+ residual gradient), optionally fused with the LayerScale backward of the branch
+// that produced this residual stream (FUSE): dbranch = gamma * dx, dgamma += sum dx * branch,
+// dbias_br += sum dbranch.
+template <typename InT, typename BrT, bool FUSE>
+__global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ w, const float* __restrict__ dres,
+                                                          float* __restrict__ dx, float* dw, float* db,
+                                                          const BrT* __restrict__ branch, const float* __restrict__ gamma,
+                                                          BrT* __restrict__ dbranch, float* dgamma, float* dbias_br,
+                                                          long long rows, int d) {
+  __shared__ float red[2][8 * 2 * kColRows];
+  const int c = threadIdx.x * 4;
+  const bool active = c < d;
+  const int nwarps = blockDim.x >> 5;
+  float4 ww = make_float4(0.f, 0.f, 0.f, 0.f), gm = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (active) {
+    ww = __ldg(reinterpret_cast<const float4*>(w + c));
+    if (FUSE && gamma != nullptr) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  }
+  float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ab = aw, ag = aw, abb = aw;
+  int buf = 0;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * kColRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kColRows) {
+    float4 g[kColRows], xh[kColRows];
+    float rs[kColRows], sums[2 * kColRows];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[0][i] = acc[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
-    float4 g[NV], xh[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 32 + lane;
-      if (c < nvec) {
-        const float4 dyv = load4(dy + row * d + 4 * c);
-        const float4 xv = load4(x + row * d + 4 * c);
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(dyv.x * ww.x, dyv.y * ww.y, dyv.z * ww.z, dyv.w * ww.w);
-        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        acc[0][i].x += dyv.x * xh[i].x; acc[0][i].y += dyv.y * xh[i].y;
-        acc[0][i].z += dyv.z * xh[i].z; acc[0][i].w += dyv.w * xh[i].w;
-        acc[1][i].x += dyv.x; acc[1][i].y += dyv.y; acc[1][i].z += dyv.z; acc[1][i].w += dyv.w;
+    for (int j = 0; j < kColRows; ++j) {
+      const long long row = r0 + j;
+      g[j] = xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rs[j] = 0.f;
+      if (row < rows && active) {
+        const float mu = __ldg(mean + row);
+        rs[j] = __ldg(rstd + row);
+        const float4 dyv = load4(dy + row * d + c);
+        const float4 xv = load4(x + row * d + c);
+        xh[j] = make_float4((xv.x - mu) * rs[j], (xv.y - mu) * rs[j], (xv.z - mu) * rs[j], (xv.w - mu) * rs[j]);
+        g[j] = make_float4(dyv.x * ww.x, dyv.y * ww.y, dyv.z * ww.z, dyv.w * ww.w);
+        aw.x += dyv.x * xh[j].x; aw.y += dyv.y * xh[j].y; aw.z += dyv.z * xh[j].z; aw.w += dyv.w * xh[j].w;
+        ab.x += dyv.x; ab.y += dyv.y; ab.z += dyv.z; ab.w += dyv.w;
       }
+      sums[2 * j] = (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      sums[2 * j + 1] = (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
     }
-    const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+    block_sums<2 * kColRows>(sums, red[buf], nwarps);
+    buf ^= 1;
+    const float invd = 1.f / d;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 32 + lane;
-      if (c < nvec) {
+    for (int j = 0; j < kColRows; ++j) {
+      const long long row = r0 + j;
+      if (row < rows && active) {
+        const float m1 = sums[2 * j] * invd, m2 = sums[2 * j + 1] * invd;
         float4 o;
-        o.x = rs * (g[i].x - m1 - xh[i].x * m2);
-        o.y = rs * (g[i].y - m1 - xh[i].y * m2);
-        o.z = rs * (g[i].z - m1 - xh[i].z * m2);
-        o.w = rs * (g[i].w - m1 - xh[i].w * m2);
+        o.x = rs[j] * (g[j].x - m1 - xh[j].x * m2);
+        o.y = rs[j] * (g[j].y - m1 - xh[j].y * m2);
+        o.z = rs[j] * (g[j].z - m1 - xh[j].z * m2);
+        o.w = rs[j] * (g[j].w - m1 - xh[j].w * m2);
         if (dres != nullptr) {
-          const float4 r = load4(dres + row * d + 4 * c);
+          const float4 r = load4(dres + row * d + c);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
-        store4(dx + row * d + 4 * c, o);
+        store4(dx + row * d + c, o);
+        if (FUSE) {
+          const float4 br = load4(branch + row * d + c);
+          float4 dbr = make_float4(o.x * gm.x, o.y * gm.y, o.z * gm.z, o.w * gm.w);
+          store4(dbranch + row * d + c, dbr);
+          if (sizeof(BrT) == 2) dbr = bf16_round4(dbr);  // the bias gradient sums what the bf16 consumer sees
+          ag.x += o.x * br.x; ag.y += o.y * br.y; ag.z += o.z * br.z; ag.w += o.w * br.w;
+          abb.x += dbr.x; abb.y += dbr.y; abb.z += dbr.z; abb.w += dbr.w;
+        }
       }
     }
   }
-  float* const dst[2] = {dw, db};
-  flush_columns<2, NV>(acc, dst, nvec, smem_cols, d);
+  if (active) {
+    red_add4(dw + c, aw);
+    red_add4(db + c, ab);
+    if (FUSE) {
+      if (dgamma != nullptr) red_add4(dgamma + c, ag);
+      if (dbias_br != nullptr) red_add4(dbias_br + c, abb);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------- LayerScale bwd
-template <typename BrT, typename OutT, int NV>
-__global__ void __launch_bounds__(kRowThreads) scale_bwd_kernel(const float* __restrict__ dx, const BrT* __restrict__ branch,
-                                                                const float* __restrict__ gamma, OutT* __restrict__ dbranch,
-                                                                float* dgamma, float* dbias, long long rows, int d) {
-  extern __shared__ float smem_cols[];
-  const int lane = threadIdx.x & 31;
-  const int nvec = d >> 2;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * kRowThreads + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * kRowThreads) >> 5;
-  float4 acc[2][NV];
+template <typename BrT>
+__global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __restrict__ dx, const BrT* __restrict__ branch,
+                                                             const float* __restrict__ gamma, BrT* __restrict__ dbranch,
+                                                             float* dgamma, float* dbias, long long rows, int d) {
+  const int c = threadIdx.x * 4;
+  if (c >= d) return;
+  float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (gamma != nullptr) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * kColRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kColRows) {
+    float4 g[kColRows], br[kColRows];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[0][i] = acc[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = warp0; row < rows; row += nwarps) {
+    for (int j = 0; j < kColRows; ++j) {
+      g[j] = br[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + j < rows) {
+        g[j] = load4(dx + (r0 + j) * d + c);
+        if (dgamma != nullptr) br[j] = load4(branch + (r0 + j) * d + c);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 32 + lane;
-      if (c < nvec) {
-        const float4 g = load4(dx + row * d + 4 * c);
-        float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gamma != nullptr) gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        float4 o = make_float4(g.x * gm.x, g.y * gm.y, g.z * gm.z, g.w * gm.w);
-        store4(dbranch + row * d + 4 * c, o);
-        if (sizeof(OutT) == 2) {  // bias gradient sums what the bf16 consumer will actually see
-          o.x = __bfloat162float(__float2bfloat16_rn(o.x)); o.y = __bfloat162float(__float2bfloat16_rn(o.y));
-          o.z = __bfloat162float(__float2bfloat16_rn(o.z)); o.w = __bfloat162float(__float2bfloat16_rn(o.w));
-        }
-        if (dgamma != nullptr) {
-          const float4 br = load4(branch + row * d + 4 * c);
-          acc[0][i].x += g.x * br.x; acc[0][i].y += g.y * br.y; acc[0][i].z += g.z * br.z; acc[0][i].w += g.w * br.w;
-        }
-        acc[1][i].x += o.x; acc[1][i].y += o.y; acc[1][i].z += o.z; acc[1][i].w += o.w;
+    for (int j = 0; j < kColRows; ++j) {
+      if (r0 + j < rows) {
+        float4 o = make_float4(g[j].x * gm.x, g[j].y * gm.y, g[j].z * gm.z, g[j].w * gm.w);
+        store4(dbranch + (r0 + j) * d + c, o);
+        if (sizeof(BrT) == 2) o = bf16_round4(o);
+        ag.x += g[j].x * br[j].x; ag.y += g[j].y * br[j].y; ag.z += g[j].z * br[j].z; ag.w += g[j].w * br[j].w;
+        ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
       }
     }
   }
-  float* const dst[2] = {dgamma, dbias};
-  flush_columns<2, NV>(acc, dst, nvec, smem_cols, d);
+  if (dgamma != nullptr) red_add4(dgamma + c, ag);
+  if (dbias != nullptr) red_add4(dbias + c, ab);
 }
 
 // ------------------------------------------------------------------------------------------- column sums
-// out[j] += sum_r x[r, j]; CTA (bx, by) covers 128 columns x a slab of rows; thread = 4 columns x 1/8 of the slab.
+// out[j] += sum_r x[r, j]; CTA (bx, by): 1024 columns x every gridDim.y-th group of 8 rows.
 template <typename T>
-__global__ void __launch_bounds__(kRowThreads) colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
-                                                             float* out) {
-  __shared__ float4 part[kRowThreads];
-  const int cv = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + cv) * 4;
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, float* out) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col < cols) {
-    for (long long r = static_cast<long long>(blockIdx.y) * 8 + ry; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
-      const float4 v = load4(x + r * ld + col);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-  }
-  part[threadIdx.x] = s;
-  __syncthreads();
-  if (ry == 0 && col < cols) {
+  for (long long r0 = static_cast<long long>(blockIdx.y) * 8; r0 < rows; r0 += static_cast<long long>(gridDim.y) * 8) {
+    float4 v[8];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      const float4 v = part[k * 32 + cv];
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    atomicAdd(out + col, s.x); atomicAdd(out + col + 1, s.y); atomicAdd(out + col + 2, s.z); atomicAdd(out + col + 3, s.w);
+    for (int j = 0; j < 8; ++j) v[j] = (r0 + j < rows) ? load4(x + (r0 + j) * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
   }
+  red_add4(out + c, s);
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
@@ -263,19 +285,46 @@ extern "C" int mome_ln_fwd(const float* x, const float* weight, const float* bia
   return check_launch("ln_fwd");
 }
 
+static int col_threads(int64_t d) { return static_cast<int>(((d / 4) + 31) / 32 * 32); }
+static int col_grid(int64_t rows, int ctas_per_sm) {
+  const long long groups = (rows + kColRows - 1) / kColRows;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(groups, static_cast<long long>(sm_count()) * ctas_per_sm)));
+}
+
+template <bool FUSE>
+static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd, const float* weight,
+                         const float* dres, float* dx_out, float* dweight, float* dbias, const void* branch, const float* gamma,
+                         void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, cudaStream_t s) {
+  const int threads = col_threads(d), grid = col_grid(rows, 4);
+  if (dy_dtype == MOME_BF16)
+    ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE><<<grid, threads, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, dweight, dbias,
+        static_cast<const __nv_bfloat16*>(branch), gamma, static_cast<__nv_bfloat16*>(dbranch), dgamma, dbias_br, rows, (int)d);
+  else
+    ln_bwd_cols_kernel<float, float, FUSE><<<grid, threads, 0, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out,
+                                                                     dweight, dbias, static_cast<const float*>(branch), gamma,
+                                                                     static_cast<float*>(dbranch), dgamma, dbias_br, rows, (int)d);
+  return check_launch(FUSE ? "ln_bwd_scale" : "ln_bwd");
+}
+
 extern "C" int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
                            const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                            int64_t rows, int64_t d, void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "ln_bwd: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
   if (rows == 0) return MOME_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(float) * (kRowThreads / 32) * d;
-  const int grid = std::min(row_grid(rows), sm_count() * 2);
-  if (dy_dtype == MOME_BF16)
-    MOME_DISPATCH_NV(d, 8, (ln_bwd_kernel<__nv_bfloat16, NV><<<grid, kRowThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, dweight, dbias, rows, (int)d)));
-  else
-    MOME_DISPATCH_NV(d, 8, (ln_bwd_kernel<float, NV><<<grid, kRowThreads, smem, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out, dweight, dbias, rows, (int)d)));
-  return check_launch("ln_bwd");
+  return ln_bwd_launch<false>(dy, dy_dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, rows, d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
+                                 const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
+                                 const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
+                                 int64_t rows, int64_t d, void* stream) {
+  MOME_REQUIRE(d % 4 == 0 && d <= 1024, "ln_bwd_scale: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
+  MOME_REQUIRE(branch != nullptr && dbranch != nullptr, "ln_bwd_scale: branch / dbranch must be given");
+  if (rows == 0) return MOME_OK;
+  return ln_bwd_launch<true>(dy, dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, branch, gamma, dbranch, dgamma,
+                             dbias_branch, rows, d, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
@@ -284,12 +333,13 @@ extern "C" int mome_scale_bwd(const float* dx, const void* branch, int branch_dt
   MOME_REQUIRE(branch_dtype == dbranch_dtype, "scale_bwd: branch and dbranch dtypes must match");
   if (rows == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(float) * (kRowThreads / 32) * d;
-  const int grid = std::min(row_grid(rows), sm_count() * 2);
+  const int threads = col_threads(d), grid = col_grid(rows, 6);
   if (branch_dtype == MOME_BF16)
-    MOME_DISPATCH_NV(d, 8, (scale_bwd_kernel<__nv_bfloat16, __nv_bfloat16, NV><<<grid, kRowThreads, smem, s>>>(dx, static_cast<const __nv_bfloat16*>(branch), gamma, static_cast<__nv_bfloat16*>(dbranch), dgamma, dbias, rows, (int)d)));
+    scale_bwd_cols_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(dx, static_cast<const __nv_bfloat16*>(branch), gamma,
+                                                                   static_cast<__nv_bfloat16*>(dbranch), dgamma, dbias, rows, (int)d);
   else
-    MOME_DISPATCH_NV(d, 8, (scale_bwd_kernel<float, float, NV><<<grid, kRowThreads, smem, s>>>(dx, static_cast<const float*>(branch), gamma, static_cast<float*>(dbranch), dgamma, dbias, rows, (int)d)));
+    scale_bwd_cols_kernel<float><<<grid, threads, 0, s>>>(dx, static_cast<const float*>(branch), gamma, static_cast<float*>(dbranch),
+                                                          dgamma, dbias, rows, (int)d);
   return check_launch("scale_bwd");
 }
 
@@ -297,13 +347,13 @@ extern "C" int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols,
   MOME_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "colsum: cols/ld must be multiples of 4");
   if (rows == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid(static_cast<unsigned>((cols + 127) / 128), 1);
-  const long long slabs = std::max<long long>(1, std::min<long long>((rows + 63) / 64, (2LL * sm_count() + grid.x - 1) / grid.x));
+  dim3 grid(static_cast<unsigned>((cols + 1023) / 1024), 1);
+  const long long slabs = std::max<long long>(1, std::min<long long>((rows + 7) / 8, (6LL * sm_count() + grid.x - 1) / grid.x));
   grid.y = static_cast<unsigned>(slabs);
   if (dtype == MOME_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, kRowThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, out);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, out);
   else
-    colsum_kernel<float><<<grid, kRowThreads, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, out);
+    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, out);
   return check_launch("colsum");
 }
 

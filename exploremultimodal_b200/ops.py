@@ -104,6 +104,7 @@ def gemm(code, a_major, b_major, epilogue, out_code, N, lda, ldb, ldo, groups, l
         s = args.group[i]
         s.a, s.b, s.M, s.K, s.out = g['a'], g['b'], g['M'], g['K'], g['out']
         s.out2, s.bias, s.res, s.aux = g.get('out2'), g.get('bias'), g.get('res'), g.get('aux')
+        s.colsum = g.get('colsum')
     L.check(L.lib().mome_gemm(C.byref(args), L.stream()), 'mome_gemm')
 
 
@@ -230,28 +231,28 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
                                        dbr2.data_ptr() + s * d * es, code, L.ptr(dgamma2), db2.data_ptr(), n, d,
                                        L.stream()), 'mome_scale_bwd')
         g_dgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=w2.data_ptr(), M=n, K=d, out=dz.data_ptr() + s * hid * es,
-                             aux=z.data_ptr() + s * hid * es))
+                             aux=z.data_ptr() + s * hid * es, colsum=db1.data_ptr()))
         g_wgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=u.data_ptr() + s * hid * es, M=d, K=n, out=dw2.data_ptr()))
         g_wgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=h2.data_ptr() + s * d * es, M=hid, K=n, out=dw1.data_ptr()))
         g_dgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=w1.data_ptr(), M=n, K=hid, out=dh2.data_ptr() + s * d * es))
-    # dz = (dbr2 @ W2) * gelu'(z); `z` holds gelu'(z), stashed by the forward GELU epilogue
+    # dz = (dbr2 @ W2) * gelu'(z); `z` holds gelu'(z), stashed by the forward GELU epilogue; db1 += colsum(dz)
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_DGELU, code, hid, d, hid, hid, g_dgrad2, ldaux=hid)
     # dW2 += dbr2^T @ u
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, hid, d, hid, hid, g_wgrad2)
-    for (s, n, route) in lay.groups:
-        colsum(dz, grads[('mlp', route)][1], s, n)
     # dW1 += dz^T @ h2 ; dh2 = dz @ W1
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, hid, d, d, g_wgrad1)
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, hid, d, d, g_dgrad1)
+    # LN2 backward (+ residual gradient dx2) fused with the LayerScale backward of the attention branch:
+    # dx1, then dbr1 = gamma_1 * dx1, dgamma_1 += dx1 * br1, dproj_b += dbr1 while dx1 is still in registers
     dn2w, dn2b = torch.zeros(d, **f32), torch.zeros(d, **f32)
-    dx1 = ln_bwd(dh2, x1, mean2, rstd2, p.n2w, dx2, dn2w, dn2b)
-
-    # ---- attention branch: x1 = x + gamma_1 * proj(attn(qkv(LN1(x))))
     dgamma1 = torch.zeros(d, **f32) if has_gamma else None
     dproj_b = torch.zeros(d, **f32)
     dbr1 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    L.check(L.lib().mome_scale_bwd(dx1.data_ptr(), br1.data_ptr(), code, L.ptr(p.gamma_1), dbr1.data_ptr(), code,
-                                   L.ptr(dgamma1), dproj_b.data_ptr(), tokens, d, L.stream()), 'mome_scale_bwd')
+    dx1 = torch.empty_like(x1)
+    L.check(L.lib().mome_ln_bwd_scale(dh2.data_ptr(), code, x1.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(),
+                                      p.n2w.data_ptr(), dx2.data_ptr(), dx1.data_ptr(), dn2w.data_ptr(), dn2b.data_ptr(),
+                                      br1.data_ptr(), L.ptr(p.gamma_1), dbr1.data_ptr(), L.ptr(dgamma1),
+                                      dproj_b.data_ptr(), tokens, d, L.stream()), 'mome_ln_bwd_scale')
     dw_proj = torch.zeros(d, d, **f32)
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, d, d, d,
          [dict(a=dbr1.data_ptr(), b=o.data_ptr(), M=d, K=tokens, out=dw_proj.data_ptr())])

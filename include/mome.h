@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MOME_ABI_VERSION 1
+#define MOME_ABI_VERSION 2
 #define MOME_MAX_GROUPS 4
 
 enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
@@ -40,6 +40,14 @@ int mome_ln_fwd(const float* x, const float* weight, const float* bias, void* y,
 int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
                 const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                 int64_t rows, int64_t d, void* stream);
+/* mome_ln_bwd fused with the LayerScale backward of the branch that produced this residual stream
+ * (x1 = x + gamma * branch, reference vlmo.py:194): besides dx_out it writes dbranch = gamma * dx_out
+ * (branch dtype) and accumulates dgamma += sum_rows dx_out * branch, dbias_branch += sum_rows dbranch.
+ * `dtype` is the dtype of dy, branch and dbranch. gamma / dgamma / dbias_branch may be NULL. */
+int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
+                      const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
+                      const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
+                      int64_t rows, int64_t d, void* stream);
 /* LayerScale backward (reference vlmo.py:194-196, `x + gamma * branch`):
  *   dbranch = gamma * dx (cast to dbranch_dtype); dgamma += sum_rows dx * branch;
  *   dbias += sum_rows dbranch (bias of the Linear that produced `branch`). gamma may be NULL (=1). */
@@ -82,6 +90,7 @@ typedef struct {
   const float* bias; /* [N] or NULL */
   const float* res;  /* fp32 [M, ldres] (RESIDUAL) */
   const void* aux;   /* operand dtype [M, ldaux] (DGELU) */
+  float* colsum;     /* optional (STORE / DGELU): colsum[n] += sum_m out[m, n] as stored  (bias gradient) */
 } MomeGemmGroup;
 
 typedef struct {

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     _ensure_built()
     handle = ctypes.CDLL(_lib.LIB_PATH)
     declared = _declared_functions()
-    assert len(declared) >= 18
+    assert len(declared) >= 19
     for name in declared:
         assert hasattr(handle, name), f'{name} declared in include/mome.h but not exported'
     assert sorted(_lib.exported_symbols()) == declared, 'ctypes binding and header disagree'
@@ -37,9 +37,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # MomeGemmGroup: 9 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
-    assert ctypes.sizeof(_lib.GemmGroup) == 72
-    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 72
+    # MomeGemmGroup: 10 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
+    assert ctypes.sizeof(_lib.GemmGroup) == 80
+    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 80
 
 
 def test_state_dict_layout_matches_reference():

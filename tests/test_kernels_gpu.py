@@ -85,6 +85,39 @@ def test_scale_bwd_and_colsum(bf16):
     assert rel_err(out2, branch[100:400].double().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('rows,d', [(5, 128), (1001, 768), (333, 1024)])
+def test_ln_bwd_scale_fused(bf16, rows, d):
+    """LN backward fused with the LayerScale backward of the producing branch == the two separate kernels."""
+    L, ops = _mods()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    code = L.BF16 if bf16 else L.F32
+    x = _rand(rows, d, seed=1) * 2 + 0.5
+    w, b = 1 + 0.1 * _rand(d, seed=2), 0.1 * _rand(d, seed=3)
+    y, mean, rstd = ops.ln_fwd(x, w, b, code, 1e-12)
+    dy = _rand(rows, d, seed=4).to(dt)
+    dres = _rand(rows, d, seed=5)
+    branch = _rand(rows, d, seed=6).to(dt)
+    gamma = 0.1 * (1 + 0.2 * _rand(d, seed=7))
+    z = lambda n: torch.zeros(n, device=_dev())
+    dw0, db0 = z(d), z(d)
+    dx0 = ops.ln_bwd(dy, x, mean, rstd, w, dres, dw0, db0)
+    dbr0 = torch.empty(rows, d, dtype=dt, device=_dev())
+    dg0, dbb0 = z(d), z(d)
+    L.check(L.lib().mome_scale_bwd(dx0.data_ptr(), branch.data_ptr(), code, gamma.data_ptr(), dbr0.data_ptr(), code,
+                                   dg0.data_ptr(), dbb0.data_ptr(), rows, d, L.stream()), 'scale_bwd')
+    dw1, db1, dg1, dbb1 = z(d), z(d), z(d), z(d)
+    dx1 = torch.empty_like(x)
+    dbr1 = torch.empty(rows, d, dtype=dt, device=_dev())
+    L.check(L.lib().mome_ln_bwd_scale(dy.data_ptr(), code, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(),
+                                      dres.data_ptr(), dx1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), branch.data_ptr(),
+                                      gamma.data_ptr(), dbr1.data_ptr(), dg1.data_ptr(), dbb1.data_ptr(), rows, d,
+                                      L.stream()), 'ln_bwd_scale')
+    assert torch.equal(dx0, dx1) and torch.equal(dbr0, dbr1)
+    for a, c in ((dw0, dw1), (db0, db1), (dg0, dg1), (dbb0, dbb1)):
+        assert rel_err(c, a) < 1e-5
+
+
 def test_cast_bf16():
     L, ops = _mods()
     src = _rand(1000 * 777 + 3, seed=9)
@@ -209,16 +242,18 @@ def test_gemm_gelu_residual_dgelu_grouped(bf16):
     # dz = (dy @ W2) * aux, aux = the stashed gelu'(z)
     dy = _rand(tot, d, dtype=dt, seed=7)
     dz = torch.empty(tot, hid, dtype=dt, device=_dev())
+    db1 = [torch.zeros(hid, device=_dev()) for _ in rows]
     g3, s = [], 0
     for i, r in enumerate(rows):
         g3.append(dict(a=dy.data_ptr() + s * d * es, b=w2[i].data_ptr(), M=r, K=d, out=dz.data_ptr() + s * hid * es,
-                       aux=z.data_ptr() + s * hid * es))
+                       aux=z.data_ptr() + s * hid * es, colsum=db1[i].data_ptr()))
         s += r
     ops.gemm(code, 0, 1, L.EPI_DGELU, code, hid, d, hid, hid, g3, ldaux=hid)
     s = 0
     for i, r in enumerate(rows):
         ref = (dy[s:s + r].double() @ w2[i].double()) * z[s:s + r].double()
         assert rel_err(dz[s:s + r], ref) < tol
+        assert rel_err(db1[i], dz[s:s + r].double().sum(0)) < 1e-4  # fused bias gradient = column sums of the stored dz
         s += r
 
 
