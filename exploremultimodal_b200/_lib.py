@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 K_MAJOR, MN_MAJOR = 0, 1
 MAX_GROUPS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GemmGroup(C.Structure):
@@ -39,10 +39,12 @@ _SIGNATURES = {
     'mome_last_error': (C.c_char_p, []),
     'mome_sm_count': (C.c_int, []),
     'mome_ln_fwd': (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _L, _L, _F, _P]),
-    'mome_ln_bwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
-    'mome_ln_bwd_scale': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
-    'mome_scale_bwd': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _L, _L, _P]),
-    'mome_colsum': (C.c_int, [_P, C.c_int, _L, _L, _L, _P, _P]),
+    'mome_ln_bwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, C.c_size_t, _P]),
+    'mome_ln_bwd_scale': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, C.c_size_t, _P]),
+    'mome_scale_bwd': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _L, _L, _P, C.c_size_t, _P]),
+    'mome_colsum': (C.c_int, [_P, C.c_int, _L, _L, _L, _P, _P, C.c_size_t, _P]),
+    'mome_colreduce': (C.c_int, [_P, _L, _L, _P, _P]),
+    'mome_reduce_ws_bytes': (C.c_size_t, [_L]),
     'mome_cast_bf16': (C.c_int, [_P, _P, _L, _P]),
     'mome_gemm': (C.c_int, [C.POINTER(GemmArgs), _P]),
     'mome_attn_fwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),

@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
         case MOME_EPI_DGELU:
           v *= g.aux[m * p.ldaux + n];
           g.out[m * p.ldo + n] = v;
-          if (g.colsum) atomicAdd(g.colsum + n, v);
+          if (g.colsum) atomicAdd(g.colsum + (m >> 5) * p.N + n, v);
           break;
         default:
           g.out[m * p.ldo + n] = v;
-          if (g.colsum) atomicAdd(g.colsum + n, v);
+          if (g.colsum) atomicAdd(g.colsum + (m >> 5) * p.N + n, v);
       }
     }
   }

@@ -18,8 +18,6 @@
 //
 // Replaces: F.linear / timm Mlp / residual adds of the reference Block (vlmo.py:76-78, 96, 190-196).
 #include <cuda.h>
-#include <stdlib.h>
-
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -28,10 +26,6 @@
 #include "ptx.cuh"
 
 namespace mome {
-
-namespace v1 {
-int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream);
-}
 
 namespace {
 
@@ -338,16 +332,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
             }
           }
           if ((EPI == MOME_EPI_STORE || EPI == MOME_EPI_DGELU) && g.colsum != nullptr) {
-            // fused bias gradient: sum the stored values over this warp's 32 rows, one red.add per column
+            // fused bias gradient, stage 1: the stored values summed over this warp's 32 rows go to row
+            // (row0 / 32) of the partials buffer (no atomics; mome_colreduce adds the parts)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
               cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
               cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
             }
-            if (rsub == 0) {
-              atomicAdd(g.colsum + col, cs.x); atomicAdd(g.colsum + col + 1, cs.y);
-              atomicAdd(g.colsum + col + 2, cs.z); atomicAdd(g.colsum + col + 3, cs.w);
-            }
+            if (rsub == 0 && row0 < g.M) *reinterpret_cast<float4*>(g.colsum + (row0 >> 5) * p.N + col) = cs;
           }
         }
         __syncwarp();
@@ -456,14 +448,6 @@ int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_
   return MOME_ERR_UNSUPPORTED;
 }
 
-bool use_v1() {
-  static const bool v = [] {
-    const char* e = getenv("MOME_GEMM_V1");
-    return e != nullptr && e[0] == '1';
-  }();
-  return v;
-}
-
 }  // namespace
 
 int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
@@ -496,12 +480,7 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     cudaEventRecord(rec.a, stream);
   }
   int rc;
-  if (use_v1()) {
-    rc = v1::gemm_bf16(a, stream);
-    for (int g = 0; g < a->num_groups && rc == MOME_OK; ++g)
-      if (a->group[g].colsum != nullptr)
-        rc = mome_colsum(a->group[g].out, a->out_dtype, a->group[g].M, a->N, a->ldo, a->group[g].colsum, stream);
-  } else {
+  {
     const int block_n = (a->N % 256 == 0) ? 256 : 128;
     GemmParams p;
     memset(&p, 0, sizeof(p));

@@ -97,8 +97,36 @@ __device__ __forceinline__ void block_sums(float (&v)[NVAL], float* red /* [nwar
   }
 }
 
-__device__ __forceinline__ void red_add4(float* dst, float4 v) {
-  atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+// Column reductions are two-stage and atomic-free: every CTA writes its partial sums to a workspace row
+// ([part][array * d + column]) and colreduce_kernel adds the parts into the outputs. (Contended red.add
+// on a few thousand addresses serialises in L2 and cost more than the streaming itself.)
+struct ColOuts {
+  float* out[4];
+  int d;
+};
+// out[a][j] += sum_p ws[p][a * d + j]; CTA = 32 columns, 8 warps stride over the parts.
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ ws, int nparts, int ncols, ColOuts o) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (j < ncols) {
+    int p = warp;
+    for (; p + 24 < nparts; p += 32) {
+      const float a = ws[static_cast<long long>(p) * ncols + j], b = ws[static_cast<long long>(p + 8) * ncols + j];
+      const float c = ws[static_cast<long long>(p + 16) * ncols + j], e = ws[static_cast<long long>(p + 24) * ncols + j];
+      s += (a + b) + (c + e);
+    }
+    for (; p < nparts; p += 8) s += ws[static_cast<long long>(p) * ncols + j];
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && j < ncols) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][lane];
+    float* dst = o.out[j / o.d];
+    if (dst != nullptr) dst[j % o.d] += s;
+  }
 }
 __device__ __forceinline__ float4 bf16_round4(float4 v) {
   return make_float4(__bfloat162float(__float2bfloat16_rn(v.x)), __bfloat162float(__float2bfloat16_rn(v.y)),
@@ -112,9 +140,9 @@ template <typename InT, typename BrT, bool FUSE>
 __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ w, const float* __restrict__ dres,
-                                                          float* __restrict__ dx, float* dw, float* db,
+                                                          float* __restrict__ dx,
                                                           const BrT* __restrict__ branch, const float* __restrict__ gamma,
-                                                          BrT* __restrict__ dbranch, float* dgamma, float* dbias_br,
+                                                          BrT* __restrict__ dbranch, float* __restrict__ ws,
                                                           long long rows, int d) {
   __shared__ float red[2][8 * 2 * kColRows];
   const int c = threadIdx.x * 4;
@@ -178,11 +206,12 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict_
     }
   }
   if (active) {
-    red_add4(dw + c, aw);
-    red_add4(db + c, ab);
+    float* part = ws + static_cast<long long>(blockIdx.x) * ((FUSE ? 4 : 2) * d) + c;
+    *reinterpret_cast<float4*>(part) = aw;
+    *reinterpret_cast<float4*>(part + d) = ab;
     if (FUSE) {
-      if (dgamma != nullptr) red_add4(dgamma + c, ag);
-      if (dbias_br != nullptr) red_add4(dbias_br + c, abb);
+      *reinterpret_cast<float4*>(part + 2 * d) = ag;
+      *reinterpret_cast<float4*>(part + 3 * d) = abb;
     }
   }
 }
@@ -191,7 +220,7 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict_
 template <typename BrT>
 __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __restrict__ dx, const BrT* __restrict__ branch,
                                                              const float* __restrict__ gamma, BrT* __restrict__ dbranch,
-                                                             float* dgamma, float* dbias, long long rows, int d) {
+                                                             bool need_dgamma, float* __restrict__ ws, long long rows, int d) {
   const int c = threadIdx.x * 4;
   if (c >= d) return;
   float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -204,7 +233,7 @@ __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __rest
       g[j] = br[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + j < rows) {
         g[j] = load4(dx + (r0 + j) * d + c);
-        if (dgamma != nullptr) br[j] = load4(branch + (r0 + j) * d + c);
+        if (need_dgamma) br[j] = load4(branch + (r0 + j) * d + c);
       }
     }
 #pragma unroll
@@ -218,14 +247,16 @@ __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __rest
       }
     }
   }
-  if (dgamma != nullptr) red_add4(dgamma + c, ag);
-  if (dbias != nullptr) red_add4(dbias + c, ab);
+  float* part = ws + static_cast<long long>(blockIdx.x) * (2 * d) + c;
+  *reinterpret_cast<float4*>(part) = ag;
+  *reinterpret_cast<float4*>(part + d) = ab;
 }
 
 // ------------------------------------------------------------------------------------------- column sums
-// out[j] += sum_r x[r, j]; CTA (bx, by): 1024 columns x every gridDim.y-th group of 8 rows.
+// ws[by][j] = sum over the CTA's rows of x[r, j]; CTA (bx, by): 1024 columns x every gridDim.y-th group of 8 rows.
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld, float* out) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
+                                                     float* __restrict__ ws) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,7 +267,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
   }
-  red_add4(out + c, s);
+  *reinterpret_cast<float4*>(ws + static_cast<long long>(blockIdx.y) * cols + c) = s;
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
@@ -290,71 +321,107 @@ static int col_grid(int64_t rows, int ctas_per_sm) {
   const long long groups = (rows + kColRows - 1) / kColRows;
   return static_cast<int>(std::max<long long>(1, std::min<long long>(groups, static_cast<long long>(sm_count()) * ctas_per_sm)));
 }
+static int colreduce_launch(const float* ws, int nparts, int ncols, const ColOuts& o, cudaStream_t s) {
+  colreduce_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(ws, nparts, ncols, o);
+  return check_launch("colreduce");
+}
+#define MOME_REQUIRE_WS(name, need)                                                                             \
+  MOME_REQUIRE(ws != nullptr && ws_bytes >= (need), "%s: workspace of %zu bytes needed (mome_reduce_ws_bytes), got %zu", \
+               name, static_cast<size_t>(need), static_cast<size_t>(ws_bytes))
+
+extern "C" size_t mome_reduce_ws_bytes(int64_t cols) {
+  // the largest stage-1 grid any row kernel uses (6 CTAs per SM) x 4 arrays of `cols` floats
+  return static_cast<size_t>(sm_count()) * 6 * 4 * static_cast<size_t>(cols) * sizeof(float);
+}
 
 template <bool FUSE>
 static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd, const float* weight,
                          const float* dres, float* dx_out, float* dweight, float* dbias, const void* branch, const float* gamma,
-                         void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, cudaStream_t s) {
+                         void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, float* ws, cudaStream_t s) {
   const int threads = col_threads(d), grid = col_grid(rows, 4);
   if (dy_dtype == MOME_BF16)
     ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE><<<grid, threads, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, dweight, dbias,
-        static_cast<const __nv_bfloat16*>(branch), gamma, static_cast<__nv_bfloat16*>(dbranch), dgamma, dbias_br, rows, (int)d);
+        static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
+        static_cast<__nv_bfloat16*>(dbranch), ws, rows, (int)d);
   else
     ln_bwd_cols_kernel<float, float, FUSE><<<grid, threads, 0, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out,
-                                                                     dweight, dbias, static_cast<const float*>(branch), gamma,
-                                                                     static_cast<float*>(dbranch), dgamma, dbias_br, rows, (int)d);
-  return check_launch(FUSE ? "ln_bwd_scale" : "ln_bwd");
+                                                                     static_cast<const float*>(branch), gamma,
+                                                                     static_cast<float*>(dbranch), ws, rows, (int)d);
+  int rc = check_launch(FUSE ? "ln_bwd_scale" : "ln_bwd");
+  if (rc != MOME_OK) return rc;
+  ColOuts o{{dweight, dbias, dgamma, dbias_br}, (int)d};
+  return colreduce_launch(ws, grid, (FUSE ? 4 : 2) * (int)d, o, s);
 }
 
 extern "C" int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
                            const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
-                           int64_t rows, int64_t d, void* stream) {
+                           int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "ln_bwd: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
+  MOME_REQUIRE_WS("ln_bwd", mome_reduce_ws_bytes(d));
   if (rows == 0) return MOME_OK;
   return ln_bwd_launch<false>(dy, dy_dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, nullptr, nullptr, nullptr, nullptr,
-                              nullptr, rows, d, static_cast<cudaStream_t>(stream));
+                              nullptr, rows, d, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
                                  const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                                  const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
-                                 int64_t rows, int64_t d, void* stream) {
+                                 int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "ln_bwd_scale: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
   MOME_REQUIRE(branch != nullptr && dbranch != nullptr, "ln_bwd_scale: branch / dbranch must be given");
+  MOME_REQUIRE_WS("ln_bwd_scale", mome_reduce_ws_bytes(d));
   if (rows == 0) return MOME_OK;
   return ln_bwd_launch<true>(dy, dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, branch, gamma, dbranch, dgamma,
-                             dbias_branch, rows, d, static_cast<cudaStream_t>(stream));
+                             dbias_branch, rows, d, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
-                              int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* stream) {
+                              int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* ws, size_t ws_bytes,
+                              void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "scale_bwd: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
   MOME_REQUIRE(branch_dtype == dbranch_dtype, "scale_bwd: branch and dbranch dtypes must match");
+  MOME_REQUIRE_WS("scale_bwd", mome_reduce_ws_bytes(d));
   if (rows == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int threads = col_threads(d), grid = col_grid(rows, 6);
+  float* w = static_cast<float*>(ws);
   if (branch_dtype == MOME_BF16)
     scale_bwd_cols_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(dx, static_cast<const __nv_bfloat16*>(branch), gamma,
-                                                                   static_cast<__nv_bfloat16*>(dbranch), dgamma, dbias, rows, (int)d);
+                                                                   static_cast<__nv_bfloat16*>(dbranch), dgamma != nullptr, w, rows, (int)d);
   else
     scale_bwd_cols_kernel<float><<<grid, threads, 0, s>>>(dx, static_cast<const float*>(branch), gamma, static_cast<float*>(dbranch),
-                                                          dgamma, dbias, rows, (int)d);
-  return check_launch("scale_bwd");
+                                                          dgamma != nullptr, w, rows, (int)d);
+  int rc = check_launch("scale_bwd");
+  if (rc != MOME_OK) return rc;
+  ColOuts o{{dgamma, dbias, nullptr, nullptr}, (int)d};
+  return colreduce_launch(w, grid, 2 * (int)d, o, s);
 }
 
-extern "C" int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream) {
+extern "C" int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* ws, size_t ws_bytes,
+                           void* stream) {
   MOME_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "colsum: cols/ld must be multiples of 4");
   if (rows == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>((cols + 1023) / 1024), 1);
   const long long slabs = std::max<long long>(1, std::min<long long>((rows + 7) / 8, (6LL * sm_count() + grid.x - 1) / grid.x));
   grid.y = static_cast<unsigned>(slabs);
+  MOME_REQUIRE_WS("colsum", static_cast<size_t>(slabs) * cols * sizeof(float));
+  float* w = static_cast<float*>(ws);
   if (dtype == MOME_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, out);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, w);
   else
-    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, out);
-  return check_launch("colsum");
+    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, w);
+  int rc = check_launch("colsum");
+  if (rc != MOME_OK) return rc;
+  ColOuts o{{out, nullptr, nullptr, nullptr}, (int)cols};
+  return colreduce_launch(w, (int)slabs, (int)cols, o, s);
+}
+
+// out[j] += sum_p partials[p][j] (second stage for partial column sums written by a GEMM epilogue)
+extern "C" int mome_colreduce(const float* partials, int64_t nparts, int64_t cols, float* out, void* stream) {
+  if (nparts == 0 || cols == 0) return MOME_OK;
+  ColOuts o{{out, nullptr, nullptr, nullptr}, (int)cols};
+  return colreduce_launch(partials, (int)nparts, (int)cols, o, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {

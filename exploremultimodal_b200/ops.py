@@ -71,6 +71,21 @@ def _tdtype(code):
     return torch.float32 if code == L.F32 else torch.bfloat16
 
 
+_WS = {}
+
+
+def reduce_ws(device, cols=4096):
+    """Persistent per-device scratch for the two-stage column reductions (see mome_reduce_ws_bytes).
+    One buffer per device: calls are issued on the current stream, in order."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WS.get(key)
+    need = int(L.lib().mome_reduce_ws_bytes(cols))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
 def ln_fwd(x, weight, bias, out_code, eps):
     rows, d = x.shape
     y = torch.empty(rows, d, dtype=_tdtype(out_code), device=x.device)
@@ -84,9 +99,10 @@ def ln_fwd(x, weight, bias, out_code, eps):
 def ln_bwd(dy, x, mean, rstd, weight, dres, dweight, dbias):
     rows, d = x.shape
     dx = torch.empty_like(x)
+    ws = reduce_ws(x.device)
     L.check(L.lib().mome_ln_bwd(dy.data_ptr(), L.dtype_code(dy), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                 weight.data_ptr(), L.ptr(dres), dx.data_ptr(), dweight.data_ptr(), dbias.data_ptr(),
-                                rows, d, L.stream()), 'mome_ln_bwd')
+                                rows, d, ws.data_ptr(), ws.numel(), L.stream()), 'mome_ln_bwd')
     return dx
 
 
@@ -129,22 +145,31 @@ def attn_bwd(qkv, out, dout, lay, key_mask, lse, num_heads, scale):
     return dqkv
 
 
-def scale_bwd(dx, branch, gamma, dgamma, dbias, first_row=0, rows=None):
+def scale_bwd(dx, branch, gamma, dbranch, dgamma, dbias, first_row=0, rows=None):
+    """dbranch = gamma * dx; dgamma += sum dx * branch; dbias += sum dbranch, over rows [first_row, first_row + rows)."""
     d = dx.shape[1]
     rows = dx.shape[0] if rows is None else rows
     code = L.dtype_code(branch)
     es = _esize(code)
-    return L.check(L.lib().mome_scale_bwd(dx.data_ptr() + first_row * d * 4, branch.data_ptr() + first_row * d * es, code,
-                                          L.ptr(gamma), None, code, L.ptr(dgamma), L.ptr(dbias), rows, d, L.stream()),
-                   'mome_scale_bwd')
+    ws = reduce_ws(dx.device)
+    L.check(L.lib().mome_scale_bwd(dx.data_ptr() + first_row * d * 4, branch.data_ptr() + first_row * d * es, code,
+                                   L.ptr(gamma), dbranch.data_ptr() + first_row * d * es, code, L.ptr(dgamma),
+                                   L.ptr(dbias), rows, d, ws.data_ptr(), ws.numel(), L.stream()), 'mome_scale_bwd')
 
 
 def colsum(x, out, first_row=0, rows=None):
     ld = x.shape[1]
     rows = x.shape[0] if rows is None else rows
     code = L.dtype_code(x)
+    ws = reduce_ws(x.device)
     L.check(L.lib().mome_colsum(x.data_ptr() + first_row * ld * _esize(code), code, rows, ld, ld, out.data_ptr(),
-                                L.stream()), 'mome_colsum')
+                                ws.data_ptr(), ws.numel(), L.stream()), 'mome_colsum')
+
+
+def colreduce(partials, out):
+    """out[j] += sum_p partials[p, j]"""
+    L.check(L.lib().mome_colreduce(partials.data_ptr(), partials.shape[0], partials.shape[1], out.data_ptr(), L.stream()),
+            'mome_colreduce')
 
 
 def cast_bf16(src, dst):
@@ -219,7 +244,7 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
     dbr2 = torch.empty(tokens, d, dtype=cdt, device=dev)
     dz = torch.empty(tokens, hid, dtype=cdt, device=dev)
     dh2 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    g_dgrad2, g_wgrad2, g_wgrad1, g_dgrad1 = [], [], [], []
+    g_dgrad2, g_wgrad2, g_wgrad1, g_dgrad1, parts = [], [], [], [], []
     for (s, n, route) in lay.groups:
         w1, b1, w2, b2 = p.experts[route][:4]
         db2 = torch.zeros(d, **f32)
@@ -227,16 +252,18 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
         dw2 = torch.zeros(d, hid, **f32)
         dw1 = torch.zeros(hid, d, **f32)
         grads[('mlp', route)] = (dw1, db1, dw2, db2)
-        L.check(L.lib().mome_scale_bwd(dx2.data_ptr() + s * d * 4, br2.data_ptr() + s * d * es, code, L.ptr(p.gamma_2),
-                                       dbr2.data_ptr() + s * d * es, code, L.ptr(dgamma2), db2.data_ptr(), n, d,
-                                       L.stream()), 'mome_scale_bwd')
+        scale_bwd(dx2, br2, p.gamma_2, dbr2, dgamma2, db2, s, n)
+        part = torch.zeros((n + 31) // 32, hid, **f32)  # per-32-row column sums of dz, written by the DGELU epilogue
+        parts.append((part, db1))
         g_dgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=w2.data_ptr(), M=n, K=d, out=dz.data_ptr() + s * hid * es,
-                             aux=z.data_ptr() + s * hid * es, colsum=db1.data_ptr()))
+                             aux=z.data_ptr() + s * hid * es, colsum=part.data_ptr()))
         g_wgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=u.data_ptr() + s * hid * es, M=d, K=n, out=dw2.data_ptr()))
         g_wgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=h2.data_ptr() + s * d * es, M=hid, K=n, out=dw1.data_ptr()))
         g_dgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=w1.data_ptr(), M=n, K=hid, out=dh2.data_ptr() + s * d * es))
     # dz = (dbr2 @ W2) * gelu'(z); `z` holds gelu'(z), stashed by the forward GELU epilogue; db1 += colsum(dz)
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_DGELU, code, hid, d, hid, hid, g_dgrad2, ldaux=hid)
+    for part, db1 in parts:
+        colreduce(part, db1)
     # dW2 += dbr2^T @ u
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, hid, d, hid, hid, g_wgrad2)
     # dW1 += dz^T @ h2 ; dh2 = dz @ W1
@@ -249,10 +276,12 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
     dproj_b = torch.zeros(d, **f32)
     dbr1 = torch.empty(tokens, d, dtype=cdt, device=dev)
     dx1 = torch.empty_like(x1)
+    ws = reduce_ws(dev)
     L.check(L.lib().mome_ln_bwd_scale(dh2.data_ptr(), code, x1.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(),
                                       p.n2w.data_ptr(), dx2.data_ptr(), dx1.data_ptr(), dn2w.data_ptr(), dn2b.data_ptr(),
                                       br1.data_ptr(), L.ptr(p.gamma_1), dbr1.data_ptr(), L.ptr(dgamma1),
-                                      dproj_b.data_ptr(), tokens, d, L.stream()), 'mome_ln_bwd_scale')
+                                      dproj_b.data_ptr(), tokens, d, ws.data_ptr(), ws.numel(), L.stream()),
+            'mome_ln_bwd_scale')
     dw_proj = torch.zeros(d, d, **f32)
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, d, d, d,
          [dict(a=dbr1.data_ptr(), b=o.data_ptr(), M=d, K=tokens, out=dw_proj.data_ptr())])

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MOME_ABI_VERSION 2
+#define MOME_ABI_VERSION 3
 #define MOME_MAX_GROUPS 4
 
 enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
@@ -36,10 +36,11 @@ int mome_sm_count(void);
  * 386,413 (final norm); eps 1e-12 from vlmo_module.py:21-23. */
 int mome_ln_fwd(const float* x, const float* weight, const float* bias, void* y, int y_dtype, float* mean,
                 float* rstd, int64_t rows, int64_t d, float eps, void* stream);
-/* dx_out = (dres ? dres : 0) + LN'(dy); dweight/dbias are ACCUMULATED (+=) in fp32. */
+/* dx_out = (dres ? dres : 0) + LN'(dy); dweight/dbias are ACCUMULATED (+=) in fp32. `ws`: see
+ * mome_reduce_ws_bytes below. */
 int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
                 const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
-                int64_t rows, int64_t d, void* stream);
+                int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream);
 /* mome_ln_bwd fused with the LayerScale backward of the branch that produced this residual stream
  * (x1 = x + gamma * branch, reference vlmo.py:194): besides dx_out it writes dbranch = gamma * dx_out
  * (branch dtype) and accumulates dgamma += sum_rows dx_out * branch, dbias_branch += sum_rows dbranch.
@@ -47,14 +48,22 @@ int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
 int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
                       const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                       const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
-                      int64_t rows, int64_t d, void* stream);
+                      int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream);
 /* LayerScale backward (reference vlmo.py:194-196, `x + gamma * branch`):
  *   dbranch = gamma * dx (cast to dbranch_dtype); dgamma += sum_rows dx * branch;
  *   dbias += sum_rows dbranch (bias of the Linear that produced `branch`). gamma may be NULL (=1). */
 int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
-                   int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* stream);
+                   int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* ws, size_t ws_bytes,
+                   void* stream);
 /* out[j] += sum_rows x[r, j]  (bias gradients of qkv / fc1) */
-int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* ws, size_t ws_bytes,
+                void* stream);
+/* out[j] += sum_p partials[p * cols + j] (second stage of a GEMM epilogue's fused column sums) */
+int mome_colreduce(const float* partials, int64_t nparts, int64_t cols, float* out, void* stream);
+/* Column reductions (dweight, dbias, dgamma, colsum) are two-stage and atomic-free: stage 1 writes per-CTA
+ * partial sums into the caller's workspace `ws`, stage 2 adds them into the outputs, both inside the
+ * call. mome_reduce_ws_bytes(cols) is enough for any of the calls above with d (or cols) <= `cols`. */
+size_t mome_reduce_ws_bytes(int64_t cols);
 /* fp32 -> bf16 cast (weights, once per optimizer step) */
 int mome_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 
@@ -90,7 +99,8 @@ typedef struct {
   const float* bias; /* [N] or NULL */
   const float* res;  /* fp32 [M, ldres] (RESIDUAL) */
   const void* aux;   /* operand dtype [M, ldaux] (DGELU) */
-  float* colsum;     /* optional (STORE / DGELU): colsum[n] += sum_m out[m, n] as stored  (bias gradient) */
+  float* colsum;     /* optional (STORE / DGELU), ZEROED fp32 [ceil(M/32), N]: row i receives the column sums of
+                        the stored out rows [32 i, 32 i + 32); mome_colreduce adds the rows (bias gradient) */
 } MomeGemmGroup;
 
 typedef struct {
