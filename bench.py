@@ -180,6 +180,8 @@ def run_mome(args):
     torch.manual_seed(0)
     model = build_model(cfg).to(dev).train()
     model.transformer.img_mask_token.requires_grad_(False)  # unused without MIM
+    for blk in model.transformer.blocks:
+        blk.fused_grad_accumulation = True  # gradients are all-reduced by this script, not by DDP hooks
     params = [p for p in model.parameters() if p.requires_grad]
     if world > 1:
         for p in model.parameters():

@@ -150,17 +150,20 @@ __device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask
 }
 
 // ------------------------------------------------------------------------------------------- forward
-// smem: Q | K0 | K1 | V0 | V1 tiles, keep[2][64]
-constexpr int kFwdSmem = 5 * kTileBytes + 2 * kT;
+// The streamed side lives in a ring of kFwdStages (K, V) tile pairs, one cp.async group per tile, all
+// stages requested up front: for N <= 256 (every pretraining shape) the whole K/V of the (sequence,
+// head) is in flight at once and the CTA pays one memory latency instead of one per tile.
+constexpr int kFwdStages = 4;
+// smem: Q | kFwdStages x (K, V) tiles, keep[kFwdStages][64]
+constexpr int kFwdSmem = (1 + 2 * kFwdStages) * kTileBytes + kFwdStages * kT;
 
 __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seq_desc,
                                                                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out,
                                                                 float* __restrict__ lse, int H, int max_seq_len, float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Qs = smem;
-  uint8_t* Ks = smem + kTileBytes;
-  uint8_t* Vs = smem + 3 * kTileBytes;
-  uint8_t* keep = smem + 5 * kTileBytes;
+  uint8_t* ring = smem + kTileBytes;  // stage s: K at ring + 2 s kTileBytes, V right after
+  uint8_t* keep = smem + (1 + 2 * kFwdStages) * kTileBytes;
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kT;
   const Seq sd = load_seq(seq_desc, s);
   const int n = sd.len0 + sd.len1;
@@ -170,11 +173,18 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int ntiles = (n + kT - 1) / kT;
 
+  auto load_stage = [&](int tile) {
+    const int slot = tile % kFwdStages;
+    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
+    load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
+    load_keep(keep + slot * kT, key_mask, sd, n, tile * kT);
+  };
   load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
-  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, 0);
-  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, 0);
-  cp_async_commit();
-  load_keep(keep, key_mask, sd, n, 0);
+#pragma unroll
+  for (int i = 0; i < kFwdStages; ++i) {
+    if (i < ntiles) load_stage(i);
+    cp_async_commit();
+  }
 
   uint32_t qf[4][4];
   float o[8][4];
@@ -183,21 +193,15 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
   const float sl2 = scale * kLog2e;
 
   for (int kt = 0; kt < ntiles; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < ntiles) {
-      load_tile_async(Ks + (buf ^ 1) * kTileBytes, qkv + d + h * kT, ld, sd, n, (kt + 1) * kT);
-      load_tile_async(Vs + (buf ^ 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, (kt + 1) * kT);
-      load_keep(keep + (buf ^ 1) * kT, key_mask, sd, n, (kt + 1) * kT);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
+    const int slot = kt % kFwdStages;
+    cp_async_wait<kFwdStages - 1>();
     __syncthreads();
     if (kt == 0) load_a_frags(qf, smem_u32(Qs), warp * 16);
 
     float sacc[8][4];
     zero_acc(sacc);
-    warp_gemm<false>(sacc, qf, smem_u32(Ks + buf * kTileBytes));
-    const uint8_t* kp = keep + buf * kT;
+    warp_gemm<false>(sacc, qf, smem_u32(ring + (2 * slot) * kTileBytes));
+    const uint8_t* kp = keep + slot * kT;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -234,8 +238,12 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
     }
     uint32_t pf[4][4];
     acc_to_a(pf, sacc);
-    warp_gemm<true>(o, pf, smem_u32(Vs + buf * kTileBytes));
-    __syncthreads();  // everyone is done with buffer `buf` before it is refilled
+    warp_gemm<true>(o, pf, smem_u32(ring + (2 * slot + 1) * kTileBytes));
+    if (kt + kFwdStages < ntiles) {
+      __syncthreads();  // everyone is done with this slot before it is refilled
+      load_stage(kt + kFwdStages);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -249,8 +257,9 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------------- backward: dq (+ delta)
-// smem: Q | dO | K0 | K1 | V0 | V1, keep[2][64], delta[64] floats
-constexpr int kDqSmem = 6 * kTileBytes + 2 * kT + kT * 4;
+constexpr int kBwdStages = 3;
+// smem: Q | dO | kBwdStages x (K, V) tiles, keep[kBwdStages][64], delta[64] floats
+constexpr int kDqSmem = (2 + 2 * kBwdStages) * kTileBytes + kBwdStages * kT + kT * 4;
 
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                                                                    const __nv_bfloat16* __restrict__ dout, const int32_t* __restrict__ seq_desc,
@@ -260,10 +269,9 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Qs = smem;
   uint8_t* Gs = smem + kTileBytes;
-  uint8_t* Ks = smem + 2 * kTileBytes;
-  uint8_t* Vs = smem + 4 * kTileBytes;
-  uint8_t* keep = smem + 6 * kTileBytes;
-  float* delta_s = reinterpret_cast<float*>(smem + 6 * kTileBytes + 2 * kT);
+  uint8_t* ring = smem + 2 * kTileBytes;
+  uint8_t* keep = smem + (2 + 2 * kBwdStages) * kTileBytes;
+  float* delta_s = reinterpret_cast<float*>(keep + kBwdStages * kT);
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kT;
   const Seq sd = load_seq(seq_desc, s);
   const int n = sd.len0 + sd.len1;
@@ -274,31 +282,37 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
   const int ntiles = (n + kT - 1) / kT;
   const long long stat0 = (static_cast<long long>(s) * H + h) * max_seq_len;
 
-  // O goes through the second K buffer (free until tile 1 is prefetched) to form delta = rowsum(dO * O)
+  auto load_stage = [&](int tile) {
+    const int slot = tile % kBwdStages;
+    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
+    load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
+    load_keep(keep + slot * kT, key_mask, sd, n, tile * kT);
+  };
   load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
   load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, q0);
-  load_tile_async(Ks + kTileBytes, out + h * kT, static_cast<long long>(d), sd, n, q0);
-  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, 0);
-  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, 0);
-  cp_async_commit();
-  load_keep(keep, key_mask, sd, n, 0);
-  cp_async_wait<0>();
-  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kBwdStages; ++i) {
+    if (i < ntiles) load_stage(i);
+    cp_async_commit();
+  }
+  // delta = rowsum(dO * O): two threads per row, 32 columns each, straight from global memory
   {
-    // two threads per row, 32 columns (4 chunks) each
     const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
     float acc = 0.f;
+    if (q0 + r < n) {
+      const long long row = seq_row(sd, q0 + r);
+      const uint4* po = reinterpret_cast<const uint4*>(out + row * d + h * kT + half * 32);
+      const uint4* pg = reinterpret_cast<const uint4*>(dout + row * d + h * kT + half * 32);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int ch = half * 4 + c;
-      const uint4 a = *reinterpret_cast<const uint4*>(Gs + r * 128 + ((ch ^ (r & 7)) << 4));
-      const uint4 b = *reinterpret_cast<const uint4*>(Ks + kTileBytes + r * 128 + ((ch ^ (r & 7)) << 4));
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = __ldg(pg + c), b = __ldg(po + c);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
-        const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-        acc += fa.x * fb.x + fa.y * fb.y;
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+          const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+          acc += fa.x * fb.x + fa.y * fb.y;
+        }
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -307,35 +321,32 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
       if (q0 + r < n) delta_ws[stat0 + q0 + r] = acc;
     }
   }
-  __syncthreads();
 
   uint32_t qf[4][4], gf[4][4];
-  load_a_frags(qf, smem_u32(Qs), warp * 16);
-  load_a_frags(gf, smem_u32(Gs), warp * 16);
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   // rows past the sequence end get lse = +inf => p = 0
   const float L0 = r0 < n ? lse[stat0 + r0] * kLog2e : INFINITY, L1 = r1 < n ? lse[stat0 + r1] * kLog2e : INFINITY;
-  const float D0 = delta_s[warp * 16 + g], D1 = delta_s[warp * 16 + g + 8];
+  float D0 = 0.f, D1 = 0.f;
   const float sl2 = scale * kLog2e;
   float dq[8][4];
   zero_acc(dq);
 
   for (int kt = 0; kt < ntiles; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < ntiles) {
-      load_tile_async(Ks + (buf ^ 1) * kTileBytes, qkv + d + h * kT, ld, sd, n, (kt + 1) * kT);
-      load_tile_async(Vs + (buf ^ 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, (kt + 1) * kT);
-      load_keep(keep + (buf ^ 1) * kT, key_mask, sd, n, (kt + 1) * kT);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
+    const int slot = kt % kBwdStages;
+    cp_async_wait<kBwdStages - 1>();
     __syncthreads();
+    if (kt == 0) {
+      load_a_frags(qf, smem_u32(Qs), warp * 16);
+      load_a_frags(gf, smem_u32(Gs), warp * 16);
+      D0 = delta_s[warp * 16 + g];
+      D1 = delta_s[warp * 16 + g + 8];
+    }
     float sacc[8][4], dp[8][4];
     zero_acc(sacc);
     zero_acc(dp);
-    warp_gemm<false>(sacc, qf, smem_u32(Ks + buf * kTileBytes));
-    warp_gemm<false>(dp, gf, smem_u32(Vs + buf * kTileBytes));
-    const uint8_t* kp = keep + buf * kT;
+    warp_gemm<false>(sacc, qf, smem_u32(ring + (2 * slot) * kTileBytes));
+    warp_gemm<false>(dp, gf, smem_u32(ring + (2 * slot + 1) * kTileBytes));
+    const uint8_t* kp = keep + slot * kT;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
@@ -348,16 +359,20 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
     }
     uint32_t dsf[4][4];
     acc_to_a(dsf, sacc);
-    warp_gemm<true>(dq, dsf, smem_u32(Ks + buf * kTileBytes));
-    __syncthreads();
+    warp_gemm<true>(dq, dsf, smem_u32(ring + (2 * slot) * kTileBytes));
+    if (kt + kBwdStages < ntiles) {
+      __syncthreads();
+      load_stage(kt + kBwdStages);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
   store_rows_bf16(dq, scale, scale, Qs, warp * 16, dqkv + h * kT, ld, sd, n, q0);
 }
 
 // ------------------------------------------------------------------------------------------- backward: dk, dv
-// smem: K | V | Q0 | Q1 | dO0 | dO1, lse[2][64], delta[2][64] floats
-constexpr int kDkvSmem = 6 * kTileBytes + 4 * kT * 4;
+// smem: K | V | kBwdStages x (Q, dO) tiles, lse[kBwdStages][64], delta[kBwdStages][64] floats
+constexpr int kDkvSmem = (2 + 2 * kBwdStages) * kTileBytes + 2 * kBwdStages * kT * 4;
 
 __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                                                                     const int32_t* __restrict__ seq_desc, const uint8_t* __restrict__ key_mask,
@@ -366,10 +381,9 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_b
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Ks = smem;
   uint8_t* Vs = smem + kTileBytes;
-  uint8_t* Qs = smem + 2 * kTileBytes;
-  uint8_t* Gs = smem + 4 * kTileBytes;
-  float* lse_s = reinterpret_cast<float*>(smem + 6 * kTileBytes);
-  float* delta_s = lse_s + 2 * kT;
+  uint8_t* ring = smem + 2 * kTileBytes;  // stage s: Q at ring + 2 s kTileBytes, dO right after
+  float* lse_s = reinterpret_cast<float*>(smem + (2 + 2 * kBwdStages) * kTileBytes);
+  float* delta_s = lse_s + kBwdStages * kT;
   const int s = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * kT;
   const Seq sd = load_seq(seq_desc, s);
   const int n = sd.len0 + sd.len1;
@@ -380,19 +394,23 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_b
   const int ntiles = (n + kT - 1) / kT;
   const long long stat0 = (static_cast<long long>(s) * H + h) * max_seq_len;
 
-  auto load_stats = [&](int buf, int t0) {
+  auto load_stage = [&](int tile) {
+    const int slot = tile % kBwdStages;
+    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + h * kT, ld, sd, n, tile * kT);
+    load_tile_async(ring + (2 * slot + 1) * kTileBytes, dout + h * kT, static_cast<long long>(d), sd, n, tile * kT);
     if (threadIdx.x < kT) {
-      const int i = t0 + threadIdx.x;
-      lse_s[buf * kT + threadIdx.x] = i < n ? lse[stat0 + i] * kLog2e : INFINITY;  // +inf => p = 0 for absent queries
-      delta_s[buf * kT + threadIdx.x] = i < n ? delta_ws[stat0 + i] : 0.f;
+      const int i = tile * kT + threadIdx.x;
+      lse_s[slot * kT + threadIdx.x] = i < n ? lse[stat0 + i] * kLog2e : INFINITY;  // +inf => p = 0 for absent queries
+      delta_s[slot * kT + threadIdx.x] = i < n ? delta_ws[stat0 + i] : 0.f;
     }
   };
   load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, k0);
   load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, k0);
-  load_tile_async(Qs, qkv + h * kT, ld, sd, n, 0);
-  load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, 0);
-  cp_async_commit();
-  load_stats(0, 0);
+#pragma unroll
+  for (int i = 0; i < kBwdStages; ++i) {
+    if (i < ntiles) load_stage(i);
+    cp_async_commit();
+  }
 
   // this thread's two key rows
   const int j0 = k0 + warp * 16 + g, j1 = j0 + 8;
@@ -405,45 +423,43 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_b
   zero_acc(dv);
 
   for (int qt = 0; qt < ntiles; ++qt) {
-    const int buf = qt & 1;
-    if (qt + 1 < ntiles) {
-      load_tile_async(Qs + (buf ^ 1) * kTileBytes, qkv + h * kT, ld, sd, n, (qt + 1) * kT);
-      load_tile_async(Gs + (buf ^ 1) * kTileBytes, dout + h * kT, static_cast<long long>(d), sd, n, (qt + 1) * kT);
-      load_stats(buf ^ 1, (qt + 1) * kT);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
+    const int slot = qt % kBwdStages;
+    cp_async_wait<kBwdStages - 1>();
     __syncthreads();
     if (qt == 0) {
       load_a_frags(kf, smem_u32(Ks), warp * 16);
       load_a_frags(vf, smem_u32(Vs), warp * 16);
     }
+    const uint32_t q_tile = smem_u32(ring + (2 * slot) * kTileBytes), g_tile = smem_u32(ring + (2 * slot + 1) * kTileBytes);
     float st[8][4], dpt[8][4];  // S^T and dP^T: rows = this warp's keys, columns = the tile's queries
     zero_acc(st);
     zero_acc(dpt);
-    warp_gemm<false>(st, kf, smem_u32(Qs + buf * kTileBytes));
-    warp_gemm<false>(dpt, vf, smem_u32(Gs + buf * kTileBytes));
-    const float* Lq = lse_s + buf * kT;
-    const float* Dq = delta_s + buf * kT;
-    float ds[8][4];
+    warp_gemm<false>(st, kf, q_tile);
+    warp_gemm<false>(dpt, vf, g_tile);
+    const float* Lq = lse_s + slot * kT;
+    const float* Dq = delta_s + slot * kT;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = nt * 8 + 2 * t;
       const float La = Lq[c], Lb = Lq[c + 1], Da = Dq[c], Db = Dq[c + 1];
       const float p00 = keep0 ? exp2f(st[nt][0] * sl2 - La) : 0.f, p01 = keep0 ? exp2f(st[nt][1] * sl2 - Lb) : 0.f;
       const float p10 = keep1 ? exp2f(st[nt][2] * sl2 - La) : 0.f, p11 = keep1 ? exp2f(st[nt][3] * sl2 - Lb) : 0.f;
-      ds[nt][0] = p00 * (dpt[nt][0] - Da);
-      ds[nt][1] = p01 * (dpt[nt][1] - Db);
-      ds[nt][2] = p10 * (dpt[nt][2] - Da);
-      ds[nt][3] = p11 * (dpt[nt][3] - Db);
+      dpt[nt][0] = p00 * (dpt[nt][0] - Da);
+      dpt[nt][1] = p01 * (dpt[nt][1] - Db);
+      dpt[nt][2] = p10 * (dpt[nt][2] - Da);
+      dpt[nt][3] = p11 * (dpt[nt][3] - Db);
       st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
     }
     uint32_t pf[4][4];
     acc_to_a(pf, st);
-    warp_gemm<true>(dv, pf, smem_u32(Gs + buf * kTileBytes));
-    acc_to_a(pf, ds);
-    warp_gemm<true>(dk, pf, smem_u32(Qs + buf * kTileBytes));
-    __syncthreads();
+    warp_gemm<true>(dv, pf, g_tile);
+    acc_to_a(pf, dpt);
+    warp_gemm<true>(dk, pf, q_tile);
+    if (qt + kBwdStages < ntiles) {
+      __syncthreads();
+      load_stage(qt + kBwdStages);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
   store_rows_bf16(dk, scale, scale, Ks, warp * 16, dqkv + d + h * kT, ld, sd, n, k0);

@@ -224,8 +224,17 @@ def block_forward(x, lay, key_mask, p):
     return x2, saved
 
 
-def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
-    """Returns (dx, grads) where grads maps parameter slots to fp32 gradient tensors."""
+def block_backward(dx2, lay, key_mask, p, saved, targets=None):
+    """Returns (dx, grads) where grads maps parameter slots to fp32 gradient tensors.
+
+    Every parameter-gradient kernel accumulates (+=). `targets` maps a slot to an existing fp32 buffer
+    (the parameter's .grad) to accumulate into directly; slots without a target get a fresh zeroed
+    buffer that autograd then adds to .grad."""
+    targets = targets or {}
+
+    def buf(slot, *shape):
+        t = targets.get(slot)
+        return t if t is not None else torch.zeros(*shape, **f32)
     (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, z, u, br2) = saved
     code = p.code
     es = _esize(code)
@@ -240,17 +249,17 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
 
     # ---- expert FFN branch: x2 = x1 + gamma_2 * (fc2(gelu(fc1(LN2(x1)))))
     has_gamma = p.gamma_1 is not None
-    dgamma2 = torch.zeros(d, **f32) if has_gamma else None
+    dgamma2 = buf('gamma_2', d) if has_gamma else None
     dbr2 = torch.empty(tokens, d, dtype=cdt, device=dev)
     dz = torch.empty(tokens, hid, dtype=cdt, device=dev)
     dh2 = torch.empty(tokens, d, dtype=cdt, device=dev)
     g_dgrad2, g_wgrad2, g_wgrad1, g_dgrad1, parts = [], [], [], [], []
     for (s, n, route) in lay.groups:
         w1, b1, w2, b2 = p.experts[route][:4]
-        db2 = torch.zeros(d, **f32)
-        db1 = torch.zeros(hid, **f32)
-        dw2 = torch.zeros(d, hid, **f32)
-        dw1 = torch.zeros(hid, d, **f32)
+        db2 = buf(('mlp', route, 3), d)
+        db1 = buf(('mlp', route, 1), hid)
+        dw2 = buf(('mlp', route, 2), d, hid)
+        dw1 = buf(('mlp', route, 0), hid, d)
         grads[('mlp', route)] = (dw1, db1, dw2, db2)
         scale_bwd(dx2, br2, p.gamma_2, dbr2, dgamma2, db2, s, n)
         part = torch.zeros((n + 31) // 32, hid, **f32)  # per-32-row column sums of dz, written by the DGELU epilogue
@@ -271,9 +280,9 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, hid, d, d, g_dgrad1)
     # LN2 backward (+ residual gradient dx2) fused with the LayerScale backward of the attention branch:
     # dx1, then dbr1 = gamma_1 * dx1, dgamma_1 += dx1 * br1, dproj_b += dbr1 while dx1 is still in registers
-    dn2w, dn2b = torch.zeros(d, **f32), torch.zeros(d, **f32)
-    dgamma1 = torch.zeros(d, **f32) if has_gamma else None
-    dproj_b = torch.zeros(d, **f32)
+    dn2w, dn2b = buf('n2w', d), buf('n2b', d)
+    dgamma1 = buf('gamma_1', d) if has_gamma else None
+    dproj_b = buf('proj_b', d)
     dbr1 = torch.empty(tokens, d, dtype=cdt, device=dev)
     dx1 = torch.empty_like(x1)
     ws = reduce_ws(dev)
@@ -282,7 +291,7 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
                                       br1.data_ptr(), L.ptr(p.gamma_1), dbr1.data_ptr(), L.ptr(dgamma1),
                                       dproj_b.data_ptr(), tokens, d, ws.data_ptr(), ws.numel(), L.stream()),
             'mome_ln_bwd_scale')
-    dw_proj = torch.zeros(d, d, **f32)
+    dw_proj = buf('w_proj', d, d)
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, d, d, d,
          [dict(a=dbr1.data_ptr(), b=o.data_ptr(), M=d, K=tokens, out=dw_proj.data_ptr())])
     do = torch.empty(tokens, d, dtype=cdt, device=dev)
@@ -291,15 +300,15 @@ def block_backward(dx2, lay, key_mask, p, saved, need_dx=True):
     dqkv = attn_bwd(qkv, o, do, lay, key_mask, lse, p.num_heads, scale)
     dqkv_bias = None
     if p.qkv_bias is not None:
-        dqkv_bias = torch.zeros(3 * d, **f32)
+        dqkv_bias = torch.zeros(3 * d, **f32)  # [dq_bias | (unused k part) | dv_bias]: split by the caller
         colsum(dqkv, dqkv_bias)
-    dw_qkv = torch.zeros(3 * d, d, **f32)
+    dw_qkv = buf('w_qkv', 3 * d, d)
     gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, 3 * d, d, d,
          [dict(a=dqkv.data_ptr(), b=h.data_ptr(), M=3 * d, K=tokens, out=dw_qkv.data_ptr())])
     dh = torch.empty(tokens, d, dtype=cdt, device=dev)
     gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, 3 * d, d, d,
          [dict(a=dqkv.data_ptr(), b=p.w_qkv.data_ptr(), M=tokens, K=3 * d, out=dh.data_ptr())])
-    dn1w, dn1b = torch.zeros(d, **f32), torch.zeros(d, **f32)
+    dn1w, dn1b = buf('n1w', d), buf('n1b', d)
     dx = ln_bwd(dh, x, mean1, rstd1, p.n1w, dx1, dn1w, dn1b)
 
     grads.update(gamma_1=dgamma1, gamma_2=dgamma2, n1w=dn1w, n1b=dn1b, n2w=dn2w, n2b=dn2b, qkv_bias=dqkv_bias,
@@ -325,18 +334,36 @@ class MomeBlockFn(torch.autograd.Function):
         ctx.has = [t is not None for t in params]
         return out
 
+    # slot names of the tensor inputs after x, in order (expert groups appended per layout)
+    SLOTS = ('gamma_1', 'gamma_2', 'n1w', 'n1b', 'n2w', 'n2b', 'q_bias', 'v_bias', 'w_qkv', 'w_proj', 'proj_b')
+
     @staticmethod
     def backward(ctx, dout):
         lay = ctx.lay
-        p = ctx.holder.block_params(lay)
+        holder = ctx.holder
+        p = holder.block_params(lay)
+        slots = list(MomeBlockFn.SLOTS)
+        for (_, _, route) in lay.groups:
+            slots += [('mlp', route, i) for i in range(4)]
+        # Fused gradient accumulation (opt-in, `holder.fused_grad_accumulation`): the kernels add straight
+        # into the parameters' existing fp32 .grad buffers and autograd gets None for them, which removes
+        # one zero-fill and one add per parameter per block call. Not compatible with DDP's autograd hooks.
+        targets = {}
+        if getattr(holder, 'fused_grad_accumulation', False):
+            for slot, prm in zip(slots, holder._param_list(lay)):
+                if (prm is not None and prm.requires_grad and prm.grad is not None and prm.grad.dtype == torch.float32
+                        and prm.grad.is_contiguous() and slot not in ('q_bias', 'v_bias')):
+                    targets[slot] = prm.grad
         with torch.no_grad():
-            dx, g = block_backward(dout, lay, ctx.key_mask, p, ctx.saved_tensors)
+            dx, g = block_backward(dout, lay, ctx.key_mask, p, ctx.saved_tensors, targets)
         d = dx.shape[1]
         dqb = g['qkv_bias']
-        out = [g['gamma_1'], g['gamma_2'], g['n1w'], g['n1b'], g['n2w'], g['n2b'],
-               dqb[:d] if dqb is not None else None, dqb[2 * d:] if dqb is not None else None,
-               g['w_qkv'], g['w_proj'], g['proj_b']]
+        vals = {'gamma_1': g['gamma_1'], 'gamma_2': g['gamma_2'], 'n1w': g['n1w'], 'n1b': g['n1b'], 'n2w': g['n2w'],
+                'n2b': g['n2b'], 'q_bias': dqb[:d] if dqb is not None else None,
+                'v_bias': dqb[2 * d:] if dqb is not None else None, 'w_qkv': g['w_qkv'], 'w_proj': g['w_proj'],
+                'proj_b': g['proj_b']}
         for (_, _, route) in lay.groups:
-            out.extend(g[('mlp', route)])
-        out = [t if has else None for t, has in zip(out, ctx.has)]
+            for i, t in enumerate(g[('mlp', route)]):
+                vals[('mlp', route, i)] = t
+        out = [None if (slot in targets or not has) else vals[slot] for slot, has in zip(slots, ctx.has)]
         return (None, None, None, dx, *out)

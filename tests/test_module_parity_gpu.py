@@ -159,3 +159,21 @@ def test_weight_cache_follows_optimizer_updates():
         blk.attn.proj.bias.mul_(0.0)
     y2, _ = blk(x, None, 'v')
     assert rel_err(y2, x) < 1e-6  # both branches contribute exactly zero now
+
+
+def test_fused_grad_accumulation_matches_autograd():
+    """Opt-in direct accumulation into .grad gives the same gradients as returning them to autograd."""
+    cfg = make_config('vlmo_unit', parity=True)
+    batch = _to_cuda(make_batch(cfg, 3, seed=9, lengths='realistic'))
+    grads = []
+    for fused in (False, True):
+        model = _build(cfg, 'bf16')
+        for blk in model.transformer.blocks:
+            blk.fused_grad_accumulation = fused
+        for p in model.parameters():
+            p.grad = torch.zeros_like(p)
+        out = model(batch)
+        sum(v for k, v in out.items() if 'task_loss' in k).backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    for k in grads[0]:
+        assert rel_err(grads[1][k], grads[0][k]) < 1e-3 or float(grads[0][k].norm()) == 0.0, k
