@@ -5,7 +5,7 @@
 // kernels, 64 keys in the dk/dv kernel; every warp owns 16 of those rows, so each product in the
 // kernel is a per-warp 16 x 64 x 64 GEMM whose A operand lives in registers and whose B operand is
 // a 64 x 64 bf16 tile in XOR-swizzled shared memory (ldmatrix, bank-conflict free). The opposite
-// side streams through a double-buffered cp.async pipeline. Softmax is online (running max / sum in
+// side streams through a multi-stage cp.async ring. Softmax is online (running max / sum in
 // the exp2 domain); probabilities never leave registers. Sequences are given as up to two row
 // ranges of the packed token buffer ([text | image] after the fusion layer), keys are dropped by
 // key_mask, query rows are never masked (reference vlmo.py:89-91).
@@ -142,12 +142,19 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
   }
 }
 
+// keep[0..63]: key j of the tile takes part; keep[64], keep[65]: every key of the first / second half does
+// (lets the consumers skip the per-element selects on full, unmasked tiles). kKeepBytes per stage.
+constexpr int kKeepBytes = kT + 16;
 __device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask, const Seq& sd, int n, int t0) {
   if (threadIdx.x < kT) {
     const int j = t0 + threadIdx.x;
-    keep[threadIdx.x] = (j < n) && (key_mask == nullptr || key_mask[seq_row(sd, j)] != 0);
+    const bool k = (j < n) && (key_mask == nullptr || key_mask[seq_row(sd, j)] != 0);
+    keep[threadIdx.x] = k;
+    const bool all = __all_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) keep[kT + (threadIdx.x >> 5)] = all;
   }
 }
+__device__ __forceinline__ bool tile_all_kept(const uint8_t* keep) { return keep[kT] != 0 && keep[kT + 1] != 0; }
 
 // ------------------------------------------------------------------------------------------- forward
 // The streamed side lives in a ring of kFwdStages (K, V) tile pairs, one cp.async group per tile, all
@@ -155,7 +162,7 @@ __device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask
 // head) is in flight at once and the CTA pays one memory latency instead of one per tile.
 constexpr int kFwdStages = 4;
 // smem: Q | kFwdStages x (K, V) tiles, keep[kFwdStages][64]
-constexpr int kFwdSmem = (1 + 2 * kFwdStages) * kTileBytes + kFwdStages * kT;
+constexpr int kFwdSmem = (1 + 2 * kFwdStages) * kTileBytes + kFwdStages * kKeepBytes;
 
 __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seq_desc,
                                                                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out,
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
     const int slot = tile % kFwdStages;
     load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
     load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
-    load_keep(keep + slot * kT, key_mask, sd, n, tile * kT);
+    load_keep(keep + slot * kKeepBytes, key_mask, sd, n, tile * kT);
   };
   load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
 #pragma unroll
@@ -201,30 +208,39 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
     float sacc[8][4];
     zero_acc(sacc);
     warp_gemm<false>(sacc, qf, smem_u32(ring + (2 * slot) * kTileBytes));
-    const uint8_t* kp = keep + slot * kT;
+    // running max is tracked on the raw scores; exp2(s * sl2 - m * sl2) is one FFMA + EX2 per element
+    const uint8_t* kp = keep + slot * kKeepBytes;
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (tile_all_kept(kp)) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
-      sacc[nt][0] = k0 ? sacc[nt][0] * sl2 : -INFINITY;
-      sacc[nt][1] = k1 ? sacc[nt][1] * sl2 : -INFINITY;
-      sacc[nt][2] = k0 ? sacc[nt][2] * sl2 : -INFINITY;
-      sacc[nt][3] = k1 ? sacc[nt][3] * sl2 : -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
+        sacc[nt][0] = k0 ? sacc[nt][0] : -INFINITY;
+        sacc[nt][1] = k1 ? sacc[nt][1] : -INFINITY;
+        sacc[nt][2] = k0 ? sacc[nt][2] : -INFINITY;
+        sacc[nt][3] = k1 ? sacc[nt][3] : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
     }
     mx0 = quad_max(mx0);
     mx1 = quad_max(mx1);
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;  // all keys masked so far
-    const float c0 = exp2f(m0 - ms0), c1 = exp2f(m1 - ms1);
+    const float ms0 = mn0 == -INFINITY ? 0.f : mn0 * sl2, ms1 = mn1 == -INFINITY ? 0.f : mn1 * sl2;  // all keys masked so far
+    const float c0 = exp2f(fmaf(m0, sl2, -ms0)), c1 = exp2f(fmaf(m1, sl2, -ms1));
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      sacc[nt][0] = exp2f(sacc[nt][0] - ms0);
-      sacc[nt][1] = exp2f(sacc[nt][1] - ms0);
-      sacc[nt][2] = exp2f(sacc[nt][2] - ms1);
-      sacc[nt][3] = exp2f(sacc[nt][3] - ms1);
+      sacc[nt][0] = exp2f(fmaf(sacc[nt][0], sl2, -ms0));
+      sacc[nt][1] = exp2f(fmaf(sacc[nt][1], sl2, -ms0));
+      sacc[nt][2] = exp2f(fmaf(sacc[nt][2], sl2, -ms1));
+      sacc[nt][3] = exp2f(fmaf(sacc[nt][3], sl2, -ms1));
       rs0 += sacc[nt][0] + sacc[nt][1];
       rs1 += sacc[nt][2] + sacc[nt][3];
     }
@@ -251,15 +267,15 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
   store_rows_bf16(o, inv0, inv1, Qs, warp * 16, out + h * kT, static_cast<long long>(d), sd, n, q0);
   if (t == 0) {
     const long long base = (static_cast<long long>(s) * H + h) * max_seq_len + q0 + warp * 16;
-    if (q0 + warp * 16 + g < n) lse[base + g] = l0 > 0.f ? (m0 + log2f(l0)) * kLn2 : -INFINITY;
-    if (q0 + warp * 16 + g + 8 < n) lse[base + g + 8] = l1 > 0.f ? (m1 + log2f(l1)) * kLn2 : -INFINITY;
+    if (q0 + warp * 16 + g < n) lse[base + g] = l0 > 0.f ? (m0 * sl2 + log2f(l0)) * kLn2 : -INFINITY;
+    if (q0 + warp * 16 + g + 8 < n) lse[base + g + 8] = l1 > 0.f ? (m1 * sl2 + log2f(l1)) * kLn2 : -INFINITY;
   }
 }
 
 // ------------------------------------------------------------------------------------------- backward: dq (+ delta)
 constexpr int kBwdStages = 3;
 // smem: Q | dO | kBwdStages x (K, V) tiles, keep[kBwdStages][64], delta[64] floats
-constexpr int kDqSmem = (2 + 2 * kBwdStages) * kTileBytes + kBwdStages * kT + kT * 4;
+constexpr int kDqSmem = (2 + 2 * kBwdStages) * kTileBytes + kBwdStages * kKeepBytes + kT * 4;
 
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                                                                    const __nv_bfloat16* __restrict__ dout, const int32_t* __restrict__ seq_desc,
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
   uint8_t* Gs = smem + kTileBytes;
   uint8_t* ring = smem + 2 * kTileBytes;
   uint8_t* keep = smem + (2 + 2 * kBwdStages) * kTileBytes;
-  float* delta_s = reinterpret_cast<float*>(keep + kBwdStages * kT);
+  float* delta_s = reinterpret_cast<float*>(keep + kBwdStages * kKeepBytes);
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kT;
   const Seq sd = load_seq(seq_desc, s);
   const int n = sd.len0 + sd.len1;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
     const int slot = tile % kBwdStages;
     load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
     load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
-    load_keep(keep + slot * kT, key_mask, sd, n, tile * kT);
+    load_keep(keep + slot * kKeepBytes, key_mask, sd, n, tile * kT);
   };
   load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
   load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, q0);
@@ -346,16 +362,26 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
     zero_acc(dp);
     warp_gemm<false>(sacc, qf, smem_u32(ring + (2 * slot) * kTileBytes));
     warp_gemm<false>(dp, gf, smem_u32(ring + (2 * slot + 1) * kTileBytes));
-    const uint8_t* kp = keep + slot * kT;
+    const uint8_t* kp = keep + slot * kKeepBytes;
+    if (tile_all_kept(kp)) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
-      const float p00 = k0 ? exp2f(sacc[nt][0] * sl2 - L0) : 0.f, p01 = k1 ? exp2f(sacc[nt][1] * sl2 - L0) : 0.f;
-      const float p10 = k0 ? exp2f(sacc[nt][2] * sl2 - L1) : 0.f, p11 = k1 ? exp2f(sacc[nt][3] * sl2 - L1) : 0.f;
-      sacc[nt][0] = p00 * (dp[nt][0] - D0);
-      sacc[nt][1] = p01 * (dp[nt][1] - D0);
-      sacc[nt][2] = p10 * (dp[nt][2] - D1);
-      sacc[nt][3] = p11 * (dp[nt][3] - D1);
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = exp2f(fmaf(sacc[nt][0], sl2, -L0)) * (dp[nt][0] - D0);
+        sacc[nt][1] = exp2f(fmaf(sacc[nt][1], sl2, -L0)) * (dp[nt][1] - D0);
+        sacc[nt][2] = exp2f(fmaf(sacc[nt][2], sl2, -L1)) * (dp[nt][2] - D1);
+        sacc[nt][3] = exp2f(fmaf(sacc[nt][3], sl2, -L1)) * (dp[nt][3] - D1);
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const bool k0 = kp[nt * 8 + 2 * t] != 0, k1 = kp[nt * 8 + 2 * t + 1] != 0;
+        const float p00 = k0 ? exp2f(fmaf(sacc[nt][0], sl2, -L0)) : 0.f, p01 = k1 ? exp2f(fmaf(sacc[nt][1], sl2, -L0)) : 0.f;
+        const float p10 = k0 ? exp2f(fmaf(sacc[nt][2], sl2, -L1)) : 0.f, p11 = k1 ? exp2f(fmaf(sacc[nt][3], sl2, -L1)) : 0.f;
+        sacc[nt][0] = p00 * (dp[nt][0] - D0);
+        sacc[nt][1] = p01 * (dp[nt][1] - D0);
+        sacc[nt][2] = p10 * (dp[nt][2] - D1);
+        sacc[nt][3] = p11 * (dp[nt][3] - D1);
+      }
     }
     uint32_t dsf[4][4];
     acc_to_a(dsf, sacc);
@@ -442,8 +468,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_b
     for (int nt = 0; nt < 8; ++nt) {
       const int c = nt * 8 + 2 * t;
       const float La = Lq[c], Lb = Lq[c + 1], Da = Dq[c], Db = Dq[c + 1];
-      const float p00 = keep0 ? exp2f(st[nt][0] * sl2 - La) : 0.f, p01 = keep0 ? exp2f(st[nt][1] * sl2 - Lb) : 0.f;
-      const float p10 = keep1 ? exp2f(st[nt][2] * sl2 - La) : 0.f, p11 = keep1 ? exp2f(st[nt][3] * sl2 - Lb) : 0.f;
+      const float p00 = keep0 ? exp2f(fmaf(st[nt][0], sl2, -La)) : 0.f, p01 = keep0 ? exp2f(fmaf(st[nt][1], sl2, -Lb)) : 0.f;
+      const float p10 = keep1 ? exp2f(fmaf(st[nt][2], sl2, -La)) : 0.f, p11 = keep1 ? exp2f(fmaf(st[nt][3], sl2, -Lb)) : 0.f;
       dpt[nt][0] = p00 * (dpt[nt][0] - Da);
       dpt[nt][1] = p01 * (dpt[nt][1] - Db);
       dpt[nt][2] = p10 * (dpt[nt][2] - Da);

@@ -18,6 +18,7 @@
 //
 // Replaces: F.linear / timm Mlp / residual adds of the reference Block (vlmo.py:76-78, 96, 190-196).
 #include <cuda.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -59,7 +60,7 @@ struct alignas(64) GemmParams {
   const float* gamma;
   long long ldo, ldo2, ldres, ldaux;
   int num_groups, total_items, n_tiles, splits;
-  int N, epilogue, out_bf16, pad;
+  int N, epilogue, out_bf16, debug;
 };
 
 struct WorkItem {
@@ -301,12 +302,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         }
+        if (p.debug & 2) continue;  // measurement knob: TMEM drain only
         float* mine = stage_w + lane * kStagePitch;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         __syncwarp();
+        if (p.debug & 1) { __syncwarp(); continue; }  // measurement knob: no global IO / epilogue math
         const int col = col_base + c * 32;
         float4 cur[8];
 #pragma unroll
@@ -491,6 +494,10 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     p.out_bf16 = a->out_dtype == MOME_BF16;
     p.ldo = a->ldo; p.ldo2 = a->ldo2; p.ldres = a->ldres; p.ldaux = a->ldaux;
     p.gamma = a->gamma;
+    {
+      static const int dbg = [] { const char* e = getenv("MOME_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+      p.debug = dbg;
+    }
     const int pairs = std::max(1, sm_count() / 2);
     long long tiles = 0, max_kb = 0;
     for (int g = 0; g < a->num_groups; ++g) {

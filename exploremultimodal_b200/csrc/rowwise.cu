@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const float* __rest
 // sums over the row) are a block reduction batched over R rows per iteration. Few registers -> several
 // CTAs per SM and R x 3 independent 128-bit loads in flight per thread, which is what an HBM-bound
 // kernel needs.
-constexpr int kColRows = 4;  // rows per iteration
+constexpr int kColRows = 4;   // rows per iteration (LayerScale backward)
+constexpr int kLnRows = 2;    // rows per iteration (LayerNorm backward: keeps registers low enough for 5-6 CTAs / SM)
 
 template <int NVAL>
 __device__ __forceinline__ void block_sums(float (&v)[NVAL], float* red /* [nwarps][NVAL] */, int nwarps) {
@@ -104,20 +105,29 @@ struct ColOuts {
   float* out[4];
   int d;
 };
-// out[a][j] += sum_p ws[p][a * d + j]; CTA = 32 columns, 8 warps stride over the parts.
+__device__ __forceinline__ float4 bf16_round4(float4 v) {
+  return make_float4(__bfloat162float(__float2bfloat16_rn(v.x)), __bfloat162float(__float2bfloat16_rn(v.y)),
+                     __bfloat162float(__float2bfloat16_rn(v.z)), __bfloat162float(__float2bfloat16_rn(v.w)));
+}
+
+// out[a][j] += sum_p ws[p][a * d + j]; CTA (bx, by) = 32 columns x every gridDim.y-th group of 8 parts
+// (one part per warp, 8 independent loads in flight per lane); slabs combine with <= 8 red.add per address.
 __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ ws, int nparts, int ncols, ColOuts o) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
+  const int stride = 8 * gridDim.y;
   float s = 0.f;
   if (j < ncols) {
-    int p = warp;
-    for (; p + 24 < nparts; p += 32) {
-      const float a = ws[static_cast<long long>(p) * ncols + j], b = ws[static_cast<long long>(p + 8) * ncols + j];
-      const float c = ws[static_cast<long long>(p + 16) * ncols + j], e = ws[static_cast<long long>(p + 24) * ncols + j];
-      s += (a + b) + (c + e);
+    int p = blockIdx.y * 8 + warp;
+    for (; p + 7 * stride < nparts; p += 8 * stride) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ws[static_cast<long long>(p + u * stride) * ncols + j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; p < nparts; p += 8) s += ws[static_cast<long long>(p) * ncols + j];
+    for (; p < nparts; p += stride) s += ws[static_cast<long long>(p) * ncols + j];
   }
   red[warp][lane] = s;
   __syncthreads();
@@ -125,26 +135,25 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
 #pragma unroll
     for (int w = 1; w < 8; ++w) s += red[w][lane];
     float* dst = o.out[j / o.d];
-    if (dst != nullptr) dst[j % o.d] += s;
+    if (dst != nullptr) {
+      if (gridDim.y == 1) dst[j % o.d] += s;
+      else atomicAdd(dst + j % o.d, s);
+    }
   }
-}
-__device__ __forceinline__ float4 bf16_round4(float4 v) {
-  return make_float4(__bfloat162float(__float2bfloat16_rn(v.x)), __bfloat162float(__float2bfloat16_rn(v.y)),
-                     __bfloat162float(__float2bfloat16_rn(v.z)), __bfloat162float(__float2bfloat16_rn(v.w)));
 }
 
 // LayerNorm backward (+ residual gradient), optionally fused with the LayerScale backward of the branch
 // that produced this residual stream (FUSE): dbranch = gamma * dx, dgamma += sum dx * branch,
 // dbias_br += sum dbranch.
 template <typename InT, typename BrT, bool FUSE>
-__global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ w, const float* __restrict__ dres,
                                                           float* __restrict__ dx,
                                                           const BrT* __restrict__ branch, const float* __restrict__ gamma,
                                                           BrT* __restrict__ dbranch, float* __restrict__ ws,
                                                           long long rows, int d) {
-  __shared__ float red[2][8 * 2 * kColRows];
+  __shared__ float red[2][8 * 2 * kLnRows];
   const int c = threadIdx.x * 4;
   const bool active = c < d;
   const int nwarps = blockDim.x >> 5;
@@ -155,11 +164,11 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict_
   }
   float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ab = aw, ag = aw, abb = aw;
   int buf = 0;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * kColRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kColRows) {
-    float4 g[kColRows], xh[kColRows];
-    float rs[kColRows], sums[2 * kColRows];
+  for (long long r0 = static_cast<long long>(blockIdx.x) * kLnRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kLnRows) {
+    float4 g[kLnRows], xh[kLnRows];
+    float rs[kLnRows], sums[2 * kLnRows];
 #pragma unroll
-    for (int j = 0; j < kColRows; ++j) {
+    for (int j = 0; j < kLnRows; ++j) {
       const long long row = r0 + j;
       g[j] = xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       rs[j] = 0.f;
@@ -176,11 +185,11 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const InT* __restrict_
       sums[2 * j] = (g[j].x + g[j].y) + (g[j].z + g[j].w);
       sums[2 * j + 1] = (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
     }
-    block_sums<2 * kColRows>(sums, red[buf], nwarps);
+    block_sums<2 * kLnRows>(sums, red[buf], nwarps);
     buf ^= 1;
     const float invd = 1.f / d;
 #pragma unroll
-    for (int j = 0; j < kColRows; ++j) {
+    for (int j = 0; j < kLnRows; ++j) {
       const long long row = r0 + j;
       if (row < rows && active) {
         const float m1 = sums[2 * j] * invd, m2 = sums[2 * j + 1] * invd;
@@ -317,12 +326,13 @@ extern "C" int mome_ln_fwd(const float* x, const float* weight, const float* bia
 }
 
 static int col_threads(int64_t d) { return static_cast<int>(((d / 4) + 31) / 32 * 32); }
-static int col_grid(int64_t rows, int ctas_per_sm) {
-  const long long groups = (rows + kColRows - 1) / kColRows;
+static int col_grid(int64_t rows, int ctas_per_sm, int rows_per_iter = kColRows) {
+  const long long groups = (rows + rows_per_iter - 1) / rows_per_iter;
   return static_cast<int>(std::max<long long>(1, std::min<long long>(groups, static_cast<long long>(sm_count()) * ctas_per_sm)));
 }
 static int colreduce_launch(const float* ws, int nparts, int ncols, const ColOuts& o, cudaStream_t s) {
-  colreduce_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(ws, nparts, ncols, o);
+  dim3 grid((ncols + 31) / 32, std::max(1, std::min(8, nparts / 64)));
+  colreduce_kernel<<<grid, 256, 0, s>>>(ws, nparts, ncols, o);
   return check_launch("colreduce");
 }
 #define MOME_REQUIRE_WS(name, need)                                                                             \
@@ -338,7 +348,7 @@ template <bool FUSE>
 static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd, const float* weight,
                          const float* dres, float* dx_out, float* dweight, float* dbias, const void* branch, const float* gamma,
                          void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, float* ws, cudaStream_t s) {
-  const int threads = col_threads(d), grid = col_grid(rows, 4);
+  const int threads = col_threads(d), grid = col_grid(rows, 5, kLnRows);
   if (dy_dtype == MOME_BF16)
     ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE><<<grid, threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
