@@ -157,10 +157,10 @@ __device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask
 __device__ __forceinline__ bool tile_all_kept(const uint8_t* keep) { return keep[kT] != 0 && keep[kT + 1] != 0; }
 
 // ------------------------------------------------------------------------------------------- forward
-// The streamed side lives in a ring of kFwdStages (K, V) tile pairs, one cp.async group per tile, all
-// stages requested up front: for N <= 256 (every pretraining shape) the whole K/V of the (sequence,
-// head) is in flight at once and the CTA pays one memory latency instead of one per tile.
-constexpr int kFwdStages = 4;
+// The streamed side lives in a ring of kFwdStages (K, V) tile pairs, one cp.async group per tile.
+// Measured (profiles/): the kernel is bound by issue slots / occupancy, not by load latency, so the ring
+// is kept shallow (2 stages, 41 KB) to fit 4 CTAs (16 warps) per SM, the limit the 128 registers allow.
+constexpr int kFwdStages = 2;
 // smem: Q | kFwdStages x (K, V) tiles, keep[kFwdStages][64]
 constexpr int kFwdSmem = (1 + 2 * kFwdStages) * kTileBytes + kFwdStages * kKeepBytes;
 
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
 // smem: K | V | kBwdStages x (Q, dO) tiles, lse[kBwdStages][64], delta[kBwdStages][64] floats
 constexpr int kDkvSmem = (2 + 2 * kBwdStages) * kTileBytes + 2 * kBwdStages * kT * 4;
 
-__global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+__global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                                                                     const int32_t* __restrict__ seq_desc, const uint8_t* __restrict__ key_mask,
                                                                     const float* __restrict__ lse, const float* __restrict__ delta_ws,
                                                                     __nv_bfloat16* __restrict__ dqkv, int H, int max_seq_len, float scale) {
@@ -457,29 +457,48 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_mma_kernel(const __nv_b
       load_a_frags(vf, smem_u32(Vs), warp * 16);
     }
     const uint32_t q_tile = smem_u32(ring + (2 * slot) * kTileBytes), g_tile = smem_u32(ring + (2 * slot + 1) * kTileBytes);
-    float st[8][4], dpt[8][4];  // S^T and dP^T: rows = this warp's keys, columns = the tile's queries
-    zero_acc(st);
-    zero_acc(dpt);
-    warp_gemm<false>(st, kf, q_tile);
-    warp_gemm<false>(dpt, vf, g_tile);
+    // S^T (rows = this warp's keys, columns = the tile's queries) -> P^T, packed to bf16 at once: it is both
+    // the A operand of dV += P^T dO and, unpacked again, the factor of dS^T (saves 16 live registers)
     const float* Lq = lse_s + slot * kT;
     const float* Dq = delta_s + slot * kT;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      const float La = Lq[c], Lb = Lq[c + 1], Da = Dq[c], Db = Dq[c + 1];
-      const float p00 = keep0 ? exp2f(fmaf(st[nt][0], sl2, -La)) : 0.f, p01 = keep0 ? exp2f(fmaf(st[nt][1], sl2, -Lb)) : 0.f;
-      const float p10 = keep1 ? exp2f(fmaf(st[nt][2], sl2, -La)) : 0.f, p11 = keep1 ? exp2f(fmaf(st[nt][3], sl2, -Lb)) : 0.f;
-      dpt[nt][0] = p00 * (dpt[nt][0] - Da);
-      dpt[nt][1] = p01 * (dpt[nt][1] - Db);
-      dpt[nt][2] = p10 * (dpt[nt][2] - Da);
-      dpt[nt][3] = p11 * (dpt[nt][3] - Db);
-      st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
-    }
     uint32_t pf[4][4];
-    acc_to_a(pf, st);
+    {
+      float st[8][4];
+      zero_acc(st);
+      warp_gemm<false>(st, kf, q_tile);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        const float La = Lq[c], Lb = Lq[c + 1];
+        st[nt][0] = keep0 ? exp2f(fmaf(st[nt][0], sl2, -La)) : 0.f;
+        st[nt][1] = keep0 ? exp2f(fmaf(st[nt][1], sl2, -Lb)) : 0.f;
+        st[nt][2] = keep1 ? exp2f(fmaf(st[nt][2], sl2, -La)) : 0.f;
+        st[nt][3] = keep1 ? exp2f(fmaf(st[nt][3], sl2, -Lb)) : 0.f;
+      }
+      acc_to_a(pf, st);
+    }
     warp_gemm<true>(dv, pf, g_tile);
-    acc_to_a(pf, dpt);
+    {
+      float dpt[8][4];
+      zero_acc(dpt);
+      warp_gemm<false>(dpt, vf, g_tile);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // pf[j] = {(nt 2j: row g), (nt 2j: row g+8), (nt 2j+1: row g), (nt 2j+1: row g+8)}, each a bf16 pair of columns
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int nt = 2 * j + h2, c = nt * 8 + 2 * t;
+          const float Da = Dq[c], Db = Dq[c + 1];
+          const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pf[j][2 * h2]));
+          const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pf[j][2 * h2 + 1]));
+          dpt[nt][0] = p0.x * (dpt[nt][0] - Da);
+          dpt[nt][1] = p0.y * (dpt[nt][1] - Db);
+          dpt[nt][2] = p1.x * (dpt[nt][2] - Da);
+          dpt[nt][3] = p1.y * (dpt[nt][3] - Db);
+        }
+      }
+      acc_to_a(pf, dpt);
+    }
     warp_gemm<true>(dk, pf, q_tile);
     if (qt + kBwdStages < ntiles) {
       __syncthreads();
