@@ -326,8 +326,7 @@ def run_mome(args):
     _lib.lib().mome_prof_enable(0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     sustained, burst, hbm, peak_src = measured_peaks()
     gemm_tflops = fl_g.value / (ms_g.value * 1e-3) / 1e12 if ms_g.value > 0 else 0.0
@@ -362,8 +361,19 @@ def run_mome(args):
         r = cpu_port_step_time(args.model, args.cpu_batch, 2, 1, args.lengths)
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs leave without tearing NCCL down: destroying a communicator that a live CUDA graph
+    still references blocked forever on the B200 box (the bench line was already printed). Everything
+    is synchronised and flushed first, so exiting the process directly is safe."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
