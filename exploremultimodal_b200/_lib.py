@@ -53,6 +53,8 @@ _SIGNATURES = {
     'mome_l2norm_bwd': (C.c_int, [_P, _P, _P, _P, _L, _L, _P]),
     'mome_itc_fwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'mome_itc_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'mome_itc_fwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'mome_itc_bwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mome_prof_enable': (C.c_int, [C.c_int]),
     'mome_prof_read': (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
     'mome_launch_count': (C.c_int64, []),

@@ -68,15 +68,33 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
+// Where the gathered features of every rank live. Either one local [world*bs, dim] array per modality
+// (filled by an NCCL all_gather), or — the in-kernel gather — `peers[r]` = rank r's symmetric
+// [2, bs, dim] buffer (0 = image, 1 = text features), read directly over NVLink with plain loads.
+struct ColSrc {
+  const float* all_i;
+  const float* all_t;
+  const float* const* peers;
+  int bs, dim;
+  // features of global column c of modality sel (0 image, 1 text)
+  __device__ __forceinline__ const float* col(int sel, int c) const {
+    if (peers != nullptr) {
+      const int r = c / bs;
+      return peers[r] + (static_cast<long long>(sel) * bs + (c - r * bs)) * dim;
+    }
+    return (sel == 0 ? all_i : all_t) + static_cast<long long>(c) * dim;
+  }
+};
+
 // logits[rr][c] = temp * <f[rr], all[c]> for the CTA's kItcRows local rows and every column c in [0, C)
-__device__ __forceinline__ void row_logits(const float* __restrict__ all, const float* sf, float* slog, int C, int dim, float temp) {
+__device__ __forceinline__ void row_logits(const ColSrc& src, int sel, const float* sf, float* slog, int C, int dim, float temp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = warp; c < C; c += kItcWarps) {
     float acc[kItcRows];
 #pragma unroll
     for (int rr = 0; rr < kItcRows; ++rr) acc[rr] = 0.f;
     for (int k = lane * 4; k < dim; k += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(all + static_cast<long long>(c) * dim + k));
+      const float4 a = *reinterpret_cast<const float4*>(src.col(sel, c) + k);
 #pragma unroll
       for (int rr = 0; rr < kItcRows; ++rr) {
         const float4 f = *reinterpret_cast<const float4*>(sf + rr * dim + k);
@@ -101,7 +119,7 @@ __device__ __forceinline__ void load_local_rows(const float* __restrict__ feat, 
 // ------------------------------------------------------------------------------------------- forward
 // grid (ceil(bs / kItcRows), 2 directions); dynamic smem: kItcRows * (dim + C) floats
 __global__ void __launch_bounds__(kItcThreads) itc_fwd_kernel(const float* __restrict__ i_feat, const float* __restrict__ t_feat,
-                                                              const float* __restrict__ all_i, const float* __restrict__ all_t, const float* __restrict__ temp_p,
+                                                              const ColSrc src, const float* __restrict__ temp_p,
                                                               int bs, int world, int rank, int dim, float* loss_sum, int32_t* correct,
                                                               float* __restrict__ lse, float* __restrict__ sim_local) {
   extern __shared__ __align__(16) float smem_itc[];
@@ -112,7 +130,7 @@ __global__ void __launch_bounds__(kItcThreads) itc_fwd_kernel(const float* __res
   float* slog = smem_itc + kItcRows * dim;
   load_local_rows(dir == 0 ? i_feat : t_feat, sf, r0, bs, dim);
   __syncthreads();
-  row_logits(dir == 0 ? all_t : all_i, sf, slog, C, dim, temp);
+  row_logits(src, dir == 0 ? 1 : 0, sf, slog, C, dim, temp);
   __syncthreads();
   for (int rr = 0; rr < kItcRows && r0 + rr < bs; ++rr) {
     const int r = r0 + rr, tcol = rank * bs + r;
@@ -146,7 +164,7 @@ __global__ void __launch_bounds__(kItcThreads) itc_fwd_kernel(const float* __res
 // d_feat[r] = temp * sum_c g[r, c] * all[c];  d_temp += sum_{r, c} g[r, c] * <f_r, a_c>
 // with g = coef * (softmax - onehot), coef = gscale * 0.5 / bs.
 __global__ void __launch_bounds__(kItcThreads) itc_bwd_rows_kernel(const float* __restrict__ i_feat, const float* __restrict__ t_feat,
-                                                                   const float* __restrict__ all_i, const float* __restrict__ all_t,
+                                                                   const ColSrc src,
                                                                    const float* __restrict__ temp_p, int bs, int world, int rank, int dim,
                                                                    const float* __restrict__ lse, const float* __restrict__ gscale_p, float* __restrict__ d_i_feat,
                                                                    float* __restrict__ d_t_feat, float* d_temp) {
@@ -157,10 +175,10 @@ __global__ void __launch_bounds__(kItcThreads) itc_bwd_rows_kernel(const float* 
   const float coef = __ldg(gscale_p) * 0.5f / bs;
   float* sf = smem_itc;
   float* slog = smem_itc + kItcRows * dim;
-  const float* all = dir == 0 ? all_t : all_i;
+  const int sel = dir == 0 ? 1 : 0;
   load_local_rows(dir == 0 ? i_feat : t_feat, sf, r0, bs, dim);
   __syncthreads();
-  row_logits(all, sf, slog, C, dim, temp);
+  row_logits(src, sel, sf, slog, C, dim, temp);
   __syncthreads();
   float dt = 0.f;
   for (int rr = 0; rr < kItcRows; ++rr) {
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(kItcThreads) itc_bwd_rows_kernel(const float* 
 #pragma unroll
     for (int rr = 0; rr < kItcRows; ++rr) acc[rr] = 0.f;
     for (int c = 0; c < C; ++c) {
-      const float a = __ldg(all + static_cast<long long>(c) * dim + k);
+      const float a = src.col(sel, c)[k];
 #pragma unroll
       for (int rr = 0; rr < kItcRows; ++rr) acc[rr] = fmaf(slog[rr * C + c], a, acc[rr]);
     }
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(kItcThreads) itc_bwd_rows_kernel(const float* 
 // ------------------------------------------------------------------------------------------- backward, column terms
 // d_all[c] = temp * sum_r g[r, c] * f_r. grid (ceil(C / kItcRows), 2); dynamic smem: kItcRows * (dim + bs) floats
 __global__ void __launch_bounds__(kItcThreads) itc_bwd_cols_kernel(const float* __restrict__ i_feat, const float* __restrict__ t_feat,
-                                                                   const float* __restrict__ all_i, const float* __restrict__ all_t,
+                                                                   const ColSrc src,
                                                                    const float* __restrict__ temp_p, int bs, int world, int rank, int dim,
                                                                    const float* __restrict__ lse, const float* __restrict__ gscale_p, float* __restrict__ d_all_i,
                                                                    float* __restrict__ d_all_t) {
@@ -208,11 +226,11 @@ __global__ void __launch_bounds__(kItcThreads) itc_bwd_cols_kernel(const float* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sa = smem_itc;                  // [kItcRows][dim] gathered rows (columns of the logit matrix)
   float* sg = smem_itc + kItcRows * dim;  // [kItcRows][bs]
-  const float* all = dir == 0 ? all_t : all_i;
+  const int sel = dir == 0 ? 1 : 0;
   const float* feat = dir == 0 ? i_feat : t_feat;
   for (int idx = threadIdx.x; idx < kItcRows * dim; idx += kItcThreads) {
     const int cc = idx / dim, k = idx - cc * dim;
-    sa[idx] = (c0 + cc < C) ? all[static_cast<long long>(c0 + cc) * dim + k] : 0.f;
+    sa[idx] = (c0 + cc < C) ? src.col(sel, c0 + cc)[k] : 0.f;
   }
   __syncthreads();
   for (int r = warp; r < bs; r += kItcWarps) {
@@ -290,38 +308,75 @@ extern "C" int mome_l2norm_bwd(const float* dy, const float* y, const float* inv
   return check_launch("l2norm_bwd");
 }
 
-extern "C" int mome_itc_fwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t, const float* temp, int32_t bs,
-                            int32_t world, int32_t rank, int32_t dim, float* loss_sum, int32_t* correct, float* lse, float* sim_local,
-                            void* stream) {
-  MOME_REQUIRE(bs > 0 && world > 0 && rank >= 0 && rank < world && dim > 0 && dim % 4 == 0, "itc_fwd: bad shape bs=%d world=%d rank=%d dim=%d", bs, world, rank, dim);
+static int itc_fwd_launch(const float* i_feat, const float* t_feat, const ColSrc& src, const float* temp, int32_t bs, int32_t world,
+                          int32_t rank, int32_t dim, float* loss_sum, int32_t* correct, float* lse, float* sim_local, cudaStream_t s) {
   const size_t smem = sizeof(float) * kItcRows * (static_cast<size_t>(dim) + static_cast<size_t>(world) * bs);
   int rc = opt_in_smem(itc_fwd_kernel, smem, "itc_fwd");
   if (rc != MOME_OK) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaMemsetAsync(loss_sum, 0, 2 * sizeof(float), s);
   cudaMemsetAsync(correct, 0, 2 * sizeof(int32_t), s);
   dim3 grid((bs + kItcRows - 1) / kItcRows, 2);
-  itc_fwd_kernel<<<grid, kItcThreads, smem, s>>>(i_feat, t_feat, all_i, all_t, temp, bs, world, rank, dim, loss_sum, correct, lse, sim_local);
+  itc_fwd_kernel<<<grid, kItcThreads, smem, s>>>(i_feat, t_feat, src, temp, bs, world, rank, dim, loss_sum, correct, lse, sim_local);
   return check_launch("itc_fwd");
 }
 
-extern "C" int mome_itc_bwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t, const float* temp, int32_t bs,
-                            int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat, float* d_t_feat,
-                            float* d_all_i, float* d_all_t, float* d_temp, void* stream) {
-  MOME_REQUIRE(bs > 0 && world > 0 && rank >= 0 && rank < world && dim > 0 && dim % 4 == 0, "itc_bwd: bad shape bs=%d world=%d rank=%d dim=%d", bs, world, rank, dim);
+static int itc_bwd_launch(const float* i_feat, const float* t_feat, const ColSrc& src, const float* temp, int32_t bs, int32_t world,
+                          int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat, float* d_t_feat,
+                          float* d_all_i, float* d_all_t, float* d_temp, cudaStream_t s) {
   const int C = world * bs;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem_r = sizeof(float) * kItcRows * (static_cast<size_t>(dim) + C);
   int rc = opt_in_smem(itc_bwd_rows_kernel, smem_r, "itc_bwd(rows)");
   if (rc != MOME_OK) return rc;
   dim3 grid_r((bs + kItcRows - 1) / kItcRows, 2);
-  itc_bwd_rows_kernel<<<grid_r, kItcThreads, smem_r, s>>>(i_feat, t_feat, all_i, all_t, temp, bs, world, rank, dim, lse, gscale, d_i_feat, d_t_feat, d_temp);
+  itc_bwd_rows_kernel<<<grid_r, kItcThreads, smem_r, s>>>(i_feat, t_feat, src, temp, bs, world, rank, dim, lse, gscale, d_i_feat, d_t_feat, d_temp);
   rc = check_launch("itc_bwd_rows");
   if (rc != MOME_OK) return rc;
   const size_t smem_c = sizeof(float) * kItcRows * (static_cast<size_t>(dim) + bs);
   rc = opt_in_smem(itc_bwd_cols_kernel, smem_c, "itc_bwd(cols)");
   if (rc != MOME_OK) return rc;
   dim3 grid_c((C + kItcRows - 1) / kItcRows, 2);
-  itc_bwd_cols_kernel<<<grid_c, kItcThreads, smem_c, s>>>(i_feat, t_feat, all_i, all_t, temp, bs, world, rank, dim, lse, gscale, d_all_i, d_all_t);
+  itc_bwd_cols_kernel<<<grid_c, kItcThreads, smem_c, s>>>(i_feat, t_feat, src, temp, bs, world, rank, dim, lse, gscale, d_all_i, d_all_t);
   return check_launch("itc_bwd_cols");
+}
+
+#define MOME_ITC_CHECK(name) \
+  MOME_REQUIRE(bs > 0 && world > 0 && rank >= 0 && rank < world && dim > 0 && dim % 4 == 0, name ": bad shape bs=%d world=%d rank=%d dim=%d", bs, world, rank, dim)
+
+extern "C" int mome_itc_fwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t, const float* temp, int32_t bs,
+                            int32_t world, int32_t rank, int32_t dim, float* loss_sum, int32_t* correct, float* lse, float* sim_local,
+                            void* stream) {
+  MOME_ITC_CHECK("itc_fwd");
+  const ColSrc src{all_i, all_t, nullptr, bs, dim};
+  return itc_fwd_launch(i_feat, t_feat, src, temp, bs, world, rank, dim, loss_sum, correct, lse, sim_local, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mome_itc_bwd(const float* i_feat, const float* t_feat, const float* all_i, const float* all_t, const float* temp, int32_t bs,
+                            int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat, float* d_t_feat,
+                            float* d_all_i, float* d_all_t, float* d_temp, void* stream) {
+  MOME_ITC_CHECK("itc_bwd");
+  const ColSrc src{all_i, all_t, nullptr, bs, dim};
+  return itc_bwd_launch(i_feat, t_feat, src, temp, bs, world, rank, dim, lse, gscale, d_i_feat, d_t_feat, d_all_i, d_all_t, d_temp,
+                        static_cast<cudaStream_t>(stream));
+}
+
+// In-kernel gather variants: `peers` is a DEVICE array of `world` pointers; peers[r] is rank r's [2, bs, dim]
+// fp32 feature buffer (0 = image, 1 = text) mapped into this process (NVLink peer / symmetric memory). The
+// kernels read the remote rows directly; the caller orders the ranks' writes and reads with barriers.
+extern "C" int mome_itc_fwd_peer(const float* i_feat, const float* t_feat, const void* peers, const float* temp, int32_t bs,
+                                 int32_t world, int32_t rank, int32_t dim, float* loss_sum, int32_t* correct, float* lse,
+                                 float* sim_local, void* stream) {
+  MOME_ITC_CHECK("itc_fwd_peer");
+  MOME_REQUIRE(peers != nullptr, "itc_fwd_peer: null peer table");
+  const ColSrc src{nullptr, nullptr, static_cast<const float* const*>(peers), bs, dim};
+  return itc_fwd_launch(i_feat, t_feat, src, temp, bs, world, rank, dim, loss_sum, correct, lse, sim_local, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mome_itc_bwd_peer(const float* i_feat, const float* t_feat, const void* peers, const float* temp, int32_t bs,
+                                 int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat,
+                                 float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream) {
+  MOME_ITC_CHECK("itc_bwd_peer");
+  MOME_REQUIRE(peers != nullptr, "itc_bwd_peer: null peer table");
+  const ColSrc src{nullptr, nullptr, static_cast<const float* const*>(peers), bs, dim};
+  return itc_bwd_launch(i_feat, t_feat, src, temp, bs, world, rank, dim, lse, gscale, d_i_feat, d_t_feat, d_all_i, d_all_t, d_temp,
+                        static_cast<cudaStream_t>(stream));
 }

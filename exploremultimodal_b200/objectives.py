@@ -55,10 +55,41 @@ def _world():
     return 1, 0
 
 
+class _PeerGather:
+    """Symmetric (NVLink peer-mapped) feature buffers for the in-kernel ITC gather.
+
+    Every rank owns a [2, bs, dim] fp32 buffer allocated with torch's symmetric-memory allocator and
+    exchanges the mappings once (`rendezvous`); afterwards K4 reads the other ranks' L2-normalised
+    features with plain loads over NVLink — no all_gather, no cat / roll (reference
+    objectives.py:401-414, 102-105). Writes and reads are separated by device-side barriers on the
+    signal pads (no host synchronisation, capturable in a CUDA graph).
+    Set MOME_ITC_GATHER=nccl to use NCCL all_gather instead."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, bs, dim, device):
+        import os
+        if os.environ.get('MOME_ITC_GATHER', 'peer') != 'peer':
+            return None
+        key = (bs, dim, str(device))
+        if key not in cls._cache:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(2, bs, dim, dtype=torch.float32, device=device)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                cls._cache[key] = (buf, hdl)
+            except Exception as e:  # no peer access on this system: NCCL all_gather path (still GPU)
+                import warnings
+                warnings.warn(f'symmetric-memory ITC gather unavailable ({e}); using NCCL all_gather')
+                cls._cache[key] = None
+        return cls._cache[key]
+
+
 class _ItcFn(torch.autograd.Function):
     """loss = (CE(i2t) + CE(t2i)) / 2 over this rank's rows against every rank's columns.
 
-    forward: all_gather of the two [bs, dim] feature blocks (NCCL) -> mome_itc_fwd.
+    forward: in-kernel gather over NVLink peer memory (_PeerGather -> mome_itc_fwd_peer), or all_gather of the
+    two [bs, dim] feature blocks (NCCL) -> mome_itc_fwd.
     backward: mome_itc_bwd -> reduce_scatter of the column terms (the reference all_reduces the full
     [W*bs, dim] gradient and slices, objectives.py:416-426) + local-row terms; d_temp.
     """
@@ -69,21 +100,34 @@ class _ItcFn(torch.autograd.Function):
         temp = temp.detach().reshape(1).float().contiguous()
         bs, dim = i_feat.shape
         world, rank = _world() if global_reduce else (1, 0)
-        if world > 1:
-            all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=i_feat.device)
-            all_t = torch.empty_like(all_i)
-            dist.all_gather_into_tensor(all_i, i_feat)
-            dist.all_gather_into_tensor(all_t, t_feat)
-        else:
-            all_i, all_t = i_feat, t_feat
         dev = i_feat.device
         loss_sum = torch.empty(2, dtype=torch.float32, device=dev)
         correct = torch.empty(2, dtype=torch.int32, device=dev)
         lse = torch.empty(2 * bs, dtype=torch.float32, device=dev)
         sim_local = torch.empty(2, bs, bs, dtype=torch.float32, device=dev)
-        L.check(L.lib().mome_itc_fwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
-                                     temp.data_ptr(), bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
-                                     lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd')
+        peer = _PeerGather.get(bs, dim, dev) if world > 1 else None
+        ctx.peer = peer
+        if peer is not None:
+            buf, hdl = peer
+            hdl.barrier(channel=0)       # every rank is done reading the previous step's features (fwd and bwd)
+            buf[0].copy_(i_feat)
+            buf[1].copy_(t_feat)
+            hdl.barrier(channel=1)       # every rank's features are in place
+            L.check(L.lib().mome_itc_fwd_peer(i_feat.data_ptr(), t_feat.data_ptr(), hdl.buffer_ptrs_dev, temp.data_ptr(),
+                                              bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
+                                              lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd_peer')
+            all_i = all_t = i_feat  # placeholders (the backward reads the peers' buffers again)
+        else:
+            if world > 1:
+                all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=dev)
+                all_t = torch.empty_like(all_i)
+                dist.all_gather_into_tensor(all_i, i_feat)
+                dist.all_gather_into_tensor(all_t, t_feat)
+            else:
+                all_i, all_t = i_feat, t_feat
+            L.check(L.lib().mome_itc_fwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
+                                         temp.data_ptr(), bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
+                                         lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd')
         ctx.save_for_backward(i_feat, t_feat, all_i, all_t, temp, lse)
         ctx.dims = (bs, dim, world, rank)
         per_dir = loss_sum / bs
@@ -98,12 +142,19 @@ class _ItcFn(torch.autograd.Function):
         dev = i_feat.device
         g = dloss.reshape(1).float().contiguous()
         d_i, d_t = torch.empty_like(i_feat), torch.empty_like(t_feat)
-        d_all_i, d_all_t = torch.empty_like(all_i), torch.empty_like(all_t)
+        d_all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=dev)
+        d_all_t = torch.empty_like(d_all_i)
         d_temp = torch.zeros(1, dtype=torch.float32, device=dev)
-        L.check(L.lib().mome_itc_bwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
-                                     temp.data_ptr(), bs, world, rank, dim, lse.data_ptr(), g.data_ptr(),
-                                     d_i.data_ptr(), d_t.data_ptr(), d_all_i.data_ptr(), d_all_t.data_ptr(),
-                                     d_temp.data_ptr(), L.stream()), 'mome_itc_bwd')
+        if ctx.peer is not None:
+            L.check(L.lib().mome_itc_bwd_peer(i_feat.data_ptr(), t_feat.data_ptr(), ctx.peer[1].buffer_ptrs_dev,
+                                              temp.data_ptr(), bs, world, rank, dim, lse.data_ptr(), g.data_ptr(),
+                                              d_i.data_ptr(), d_t.data_ptr(), d_all_i.data_ptr(), d_all_t.data_ptr(),
+                                              d_temp.data_ptr(), L.stream()), 'mome_itc_bwd_peer')
+        else:
+            L.check(L.lib().mome_itc_bwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
+                                         temp.data_ptr(), bs, world, rank, dim, lse.data_ptr(), g.data_ptr(),
+                                         d_i.data_ptr(), d_t.data_ptr(), d_all_i.data_ptr(), d_all_t.data_ptr(),
+                                         d_temp.data_ptr(), L.stream()), 'mome_itc_bwd')
         if world > 1:
             own_i, own_t = torch.empty_like(i_feat), torch.empty_like(t_feat)
             dist.reduce_scatter_tensor(own_i, d_all_i)

@@ -156,6 +156,18 @@ int mome_itc_bwd(const float* i_feat, const float* t_feat, const float* all_i, c
                  const float* gscale,
                  float* d_i_feat, float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream);
 
+/* In-kernel gather variants of the two calls above: instead of gathered arrays they take `peers`, a DEVICE
+ * array of `world` pointers, peers[r] = rank r's fp32 [2, bs, dim] feature buffer (0 = image, 1 = text)
+ * mapped into this process (NVLink peer access / symmetric memory). The kernels load the remote rows
+ * directly, which replaces GatherLayer.forward's all_gather + cat + roll (objectives.py:401-414, 102-105);
+ * the caller separates the ranks' buffer writes from these reads with barriers. */
+int mome_itc_fwd_peer(const float* i_feat, const float* t_feat, const void* peers, const float* temp, int32_t bs,
+                      int32_t world, int32_t rank, int32_t dim, float* loss_sum, int32_t* correct, float* lse,
+                      float* sim_local, void* stream);
+int mome_itc_bwd_peer(const float* i_feat, const float* t_feat, const void* peers, const float* temp, int32_t bs,
+                      int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat,
+                      float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream);
+
 /* ---- measurement hooks (bench.py): CUDA-event timing of every mome_gemm launch on its own stream */
 int mome_prof_enable(int on);
 /* Synchronises the recorded events; returns launches, summed milliseconds and summed FLOPs. */

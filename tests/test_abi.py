@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     _ensure_built()
     handle = ctypes.CDLL(_lib.LIB_PATH)
     declared = _declared_functions()
-    assert len(declared) >= 21
+    assert len(declared) >= 23
     for name in declared:
         assert hasattr(handle, name), f'{name} declared in include/mome.h but not exported'
     assert sorted(_lib.exported_symbols()) == declared, 'ctypes binding and header disagree'
