@@ -18,6 +18,8 @@
 //
 // Replaces: F.linear / timm Mlp / residual adds of the reference Block (vlmo.py:76-78, 96, 190-196).
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <mutex>
@@ -93,60 +95,31 @@ __device__ __forceinline__ float4 unpack4_bf16(uint2 u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// Operand a fused epilogue reads from global memory besides the accumulator (4 columns of one row):
-// the fp32 residual (RESIDUAL) or the stashed bf16 gelu'(z) (DGELU). Loaded a chunk ahead of its use.
-template <int EPI>
-struct EpiExtra {
-  float4 v;
-  __device__ __forceinline__ void load(const GemmParams& p, const GemmGroupDev& g, long long row, int col) {
-    if (EPI == MOME_EPI_RESIDUAL) {
-      v = *reinterpret_cast<const float4*>(g.res + row * p.ldres + col);
-    } else if (EPI == MOME_EPI_DGELU) {
-      v = unpack4_bf16(*reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.aux) + row * p.ldaux + col));
-    }
-  }
-};
+// bf16x2 <-> fp32 helpers of the epilogue
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
-// Fused epilogue for 4 consecutive columns [col, col+4) of one output row. `b4` / `gm4` are the bias and
-// LayerScale values of those columns (hoisted by the caller), `ex` the prefetched residual / gelu'.
-template <int EPI>
-__device__ __forceinline__ float4 epilogue4(const GemmParams& p, const GemmGroupDev& g, float4 v, long long row, int col, float4 b4,
-                                            float4 gm4, float4 ex) {
-  if (EPI == MOME_EPI_ATOMIC) {
-    atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col), v);
-    return v;
-  }
-  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-  if (EPI == MOME_EPI_GELU) {
-    // z is rounded to bf16 first (what an autocast Linear hands to GELU); out = gelu(z), out2 = gelu'(z)
-    float4 u, du;
-    gelu_fast(bf16_round(v.x), u.x, du.x);
-    gelu_fast(bf16_round(v.y), u.y, du.y);
-    gelu_fast(bf16_round(v.z), u.z, du.z);
-    gelu_fast(bf16_round(v.w), u.w, du.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(u);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col) = pack4_bf16(du);
-    return u;
-  }
-  if (EPI == MOME_EPI_RESIDUAL) {
-    // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
-    v = make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
-    if (g.out2 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + row * p.ldo2 + col) = pack4_bf16(v);
-    float4 r = ex;
-    r.x = fmaf(gm4.x, v.x, r.x); r.y = fmaf(gm4.y, v.y, r.y); r.z = fmaf(gm4.z, v.z, r.z); r.w = fmaf(gm4.w, v.w, r.w);
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = r;
-    return r;
-  }
-  if (EPI == MOME_EPI_DGELU) {
-    v.x *= ex.x; v.y *= ex.y; v.z *= ex.z; v.w *= ex.w;
-  }
-  if (p.out_bf16) {
-    v = make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + row * p.ldo + col) = pack4_bf16(v);
-  } else {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + row * p.ldo + col) = v;
-  }
-  return v;
+// GELU(erf) and its derivative for two elements at once in packed fp16 (HFMA2 / MUFU.f16x2): half the issue
+// slots of the fp32 form. Abramowitz-Stegun 7.1.26 erf; fp16 arithmetic keeps ~3 decimal digits, below the
+// bf16 resolution of the two outputs it feeds (gelu(z) and gelu'(z) are stored as bf16).
+__device__ __forceinline__ void gelu_fast2(float z0, float z1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
+  const __half2 z = __floats2half2_rn(z0, z1);
+  const __half2 a = __hmul2(__habs2(z), __float2half2_rn(0.70710678f));
+  const __half2 t = h2rcp(__hfma2(__float2half2_rn(0.3275911f), a, __float2half2_rn(1.f)));
+  const __half2 e = h2exp(__hmul2(__hmul2(z, z), __float2half2_rn(-0.5f)));
+  __half2 poly = __hfma2(t, __float2half2_rn(1.061405429f), __float2half2_rn(-1.453152027f));
+  poly = __hfma2(poly, t, __float2half2_rn(1.421413741f));
+  poly = __hfma2(poly, t, __float2half2_rn(-0.284496736f));
+  poly = __hfma2(poly, t, __float2half2_rn(0.254829592f));
+  const __half2 erf_abs = __hfma2(__hneg2(__hmul2(poly, t)), e, __float2half2_rn(1.f));
+  // copysign(erf_abs, z): move z's sign bits over
+  const uint32_t zs = *reinterpret_cast<const uint32_t*>(&z) & 0x80008000u;
+  const uint32_t es = (*reinterpret_cast<const uint32_t*>(&erf_abs) & 0x7fff7fffu) | zs;
+  const __half2 cdf = __hfma2(__float2half2_rn(0.5f), *reinterpret_cast<const __half2*>(&es), __float2half2_rn(0.5f));
+  const __half2 g = __hmul2(z, cdf);
+  const __half2 dg = __hfma2(__hmul2(z, e), __float2half2_rn(0.39894228f), cdf);
+  const float2 gf = __half22float2(g), dgf = __half22float2(dg);
+  g_bf16x2 = pack_bf16(gf.x, gf.y);
+  dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
 }
 
 template <int BLOCK_N>
@@ -276,25 +249,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
     for (int item = pair; item < p.total_items; item += num_pairs) {
       const WorkItem w = decode_item(p, item);
       if (w.kb0 >= w.kb1) continue;
-      const GemmGroupDev& g = p.g[w.g];
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tcgen05_fence_after();
+      // ---- per-item setup: group fields into registers, running byte pointers at (row0 + rsub, col_base),
+      // number of this lane's 8 row-iterations that fall inside the group
+      const GemmGroupDev g = p.g[w.g];
       const long long row0 = static_cast<long long>(w.m_tile) * PAIR_M + cta_rank * CTA_M + quarter * 32;
       constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
-      constexpr bool kHasExtra = EPI == MOME_EPI_RESIDUAL || EPI == MOME_EPI_DGELU;
       const int col_base = w.n_tile * BLOCK_N + half * (BLOCK_N / 2) + c4;
-      // residual / gelu' operands of chunk 0 (the later chunks are fetched one chunk ahead, below)
-      EpiExtra<EPI> nxt[8];
-      if (kHasExtra && col_base < p.N) {
+      const long long rfirst = row0 + rsub;
+      const int nvalid = static_cast<int>(max(0LL, min(8LL, (static_cast<long long>(g.M) - rfirst + 3) >> 2)));
+      const int nchunks = max(0, min(kChunks, (p.N - col_base + 31) >> 5));  // chunks inside N (N % 32 == 0)
+      const int osize = (EPI == MOME_EPI_ATOMIC || EPI == MOME_EPI_RESIDUAL || !p.out_bf16) ? 4 : 2;
+      char* out_p = static_cast<char*>(g.out) + (rfirst * p.ldo + col_base) * osize;
+      const long long out_step = 4 * p.ldo * osize;
+      char* out2_p = static_cast<char*>(g.out2) + (rfirst * p.ldo2 + col_base) * 2;
+      const long long out2_step = 4 * p.ldo2 * 2;
+      const bool has_out2 = g.out2 != nullptr;
+      const bool do_cs = (EPI == MOME_EPI_STORE || EPI == MOME_EPI_DGELU) && g.colsum != nullptr;
+
+      // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
+      // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
+      // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use.
+      constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < 2 ? kChunks : 2) : 1;
+      constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
+      uint2 aux[kAuxDepth][8];
+      float4 res[kResDepth][8];
+      if (EPI == MOME_EPI_DGELU) {
+        const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
+        const long long astep = 4 * p.ldaux * 2;
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-          if (row0 + it * 4 + rsub < g.M) nxt[it].load(p, g, row0 + it * 4 + rsub, col_base);
+        for (int c = 0; c < kAuxDepth; ++c) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (it < nvalid && c < nchunks) aux[c][it] = *reinterpret_cast<const uint2*>(ap + it * astep + c * 64);
+        }
       }
-#pragma unroll 1
+      const char* res_p = static_cast<const char*>(static_cast<const void*>(g.res)) + (rfirst * p.ldres + col_base) * 4;
+      const long long res_step = 4 * p.ldres * 4;
+      if (EPI == MOME_EPI_RESIDUAL) {
+#pragma unroll
+        for (int c = 0; c < kResDepth && c < kChunks; ++c) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (it < nvalid && c < nchunks) res[c][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + c * 128);
+        }
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+#pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        const int tcol = half * (BLOCK_N / 2) + c * 32;
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + tcol, r);
+        tmem_ld_32x32(tacc + c * 32, r);
         tmem_ld_wait();
         if (c == kChunks - 1) {
           // all of this warp's accumulator reads are done: hand the TMEM stage back to the MMA issuer
@@ -309,41 +315,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
           *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         __syncwarp();
-        if (p.debug & 1) { __syncwarp(); continue; }  // measurement knob: no global IO / epilogue math
+        if ((p.debug & 1) || c >= nchunks) { __syncwarp(); continue; }  // knob: no epilogue math / global IO
         const int col = col_base + c * 32;
-        float4 cur[8];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (EPI != MOME_EPI_ATOMIC && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+        if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* lds_p = stage_w + rsub * kStagePitch + c4;
+        char* op = out_p + c * 32 * osize;
+        char* o2p = out2_p + c * 64;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) cur[it] = nxt[it].v;
-        if (kHasExtra && c + 1 < kChunks && col + 32 < p.N) {
+        for (int it = 0; it < 8; ++it) {
+          if (it < nvalid) {
+            float4 v = *reinterpret_cast<const float4*>(lds_p + it * 4 * kStagePitch);
+            if (EPI == MOME_EPI_ATOMIC) {
+              atomicAdd(reinterpret_cast<float4*>(op), v);
+            } else {
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              if (EPI == MOME_EPI_GELU) {
+                // z is rounded to bf16 first (what an autocast Linear hands to GELU); out = gelu(z), out2 = gelu'(z)
+                const uint32_t z01 = pack_bf16(v.x, v.y), z23 = pack_bf16(v.z, v.w);
+                const float2 za = unpack_bf16x2(z01), zb = unpack_bf16x2(z23);
+                uint2 u, du;
+                gelu_fast2(za.x, za.y, u.x, du.x);
+                gelu_fast2(zb.x, zb.y, u.y, du.y);
+                *reinterpret_cast<uint2*>(op) = u;
+                *reinterpret_cast<uint2*>(o2p) = du;
+              } else if (EPI == MOME_EPI_RESIDUAL) {
+                // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
+                const uint2 bb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                if (has_out2) *reinterpret_cast<uint2*>(o2p) = bb;
+                const float2 ba = unpack_bf16x2(bb.x), bc = unpack_bf16x2(bb.y);
+                float4 rr = res[c % kResDepth][it];
+                rr.x = fmaf(gm4.x, ba.x, rr.x); rr.y = fmaf(gm4.y, ba.y, rr.y);
+                rr.z = fmaf(gm4.z, bc.x, rr.z); rr.w = fmaf(gm4.w, bc.y, rr.w);
+                *reinterpret_cast<float4*>(op) = rr;
+              } else {
+                if (EPI == MOME_EPI_DGELU) {
+                  const float2 a0 = unpack_bf16x2(aux[c % kAuxDepth][it].x), a1 = unpack_bf16x2(aux[c % kAuxDepth][it].y);
+                  v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
+                }
+                if (osize == 2) {
+                  const uint2 ob = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                  *reinterpret_cast<uint2*>(op) = ob;
+                  if (do_cs) {
+                    const float2 oa = unpack_bf16x2(ob.x), oc = unpack_bf16x2(ob.y);
+                    cs.x += oa.x; cs.y += oa.y; cs.z += oc.x; cs.w += oc.y;
+                  }
+                } else {
+                  *reinterpret_cast<float4*>(op) = v;
+                  if (do_cs) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
+                }
+              }
+            }
+          }
+          op += out_step;
+          o2p += out2_step;
+        }
+        if (EPI == MOME_EPI_DGELU && c + kAuxDepth < kChunks) {
+          const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
+          const long long astep = 4 * p.ldaux * 2;
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            if (row0 + it * 4 + rsub < g.M) nxt[it].load(p, g, row0 + it * 4 + rsub, col + 32);
+            if (it < nvalid && c + kAuxDepth < nchunks)
+              aux[c % kAuxDepth][it] = *reinterpret_cast<const uint2*>(ap + it * astep + (c + kAuxDepth) * 64);
         }
-        if (col < p.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (EPI != MOME_EPI_ATOMIC && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-          if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == MOME_EPI_RESIDUAL && c + kResDepth < kChunks) {
+          // the slot just consumed is refilled with the residual of chunk c + 2
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const long long row = row0 + rr;
-            if (row < g.M) {
-              const float4 v = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + c4);
-              const float4 o = epilogue4<EPI>(p, g, v, row, col, b4, gm4, cur[it]);
-              cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
-            }
-          }
-          if ((EPI == MOME_EPI_STORE || EPI == MOME_EPI_DGELU) && g.colsum != nullptr) {
-            // fused bias gradient, stage 1: the stored values summed over this warp's 32 rows go to row
-            // (row0 / 32) of the partials buffer (no atomics; mome_colreduce adds the parts)
+          for (int it = 0; it < 8; ++it)
+            if (it < nvalid && c + kResDepth < nchunks)
+              res[c % kResDepth][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + (c + kResDepth) * 128);
+        }
+        if (do_cs) {
+          // fused bias gradient, stage 1: the stored values summed over this warp's 32 rows go to row
+          // (row0 / 32) of the partials buffer (no atomics; mome_colreduce adds the parts)
 #pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-            }
-            if (rsub == 0 && row0 < g.M) *reinterpret_cast<float4*>(g.colsum + (row0 >> 5) * p.N + col) = cs;
+          for (int o = 8; o <= 16; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
           }
+          if (rsub == 0 && row0 < g.M) *reinterpret_cast<float4*>(g.colsum + (row0 >> 5) * p.N + col) = cs;
         }
         __syncwarp();
       }
