@@ -98,25 +98,24 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // bf16x2 <-> fp32 helpers of the epilogue
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
-// GELU(erf) and its derivative for two elements at once in packed fp16 (HFMA2 / MUFU.f16x2): half the issue
-// slots of the fp32 form. Abramowitz-Stegun 7.1.26 erf; fp16 arithmetic keeps ~3 decimal digits, below the
-// bf16 resolution of the two outputs it feeds (gelu(z) and gelu'(z) are stored as bf16).
+// GELU and its derivative for two elements at once in packed fp16 (HFMA2 + two MUFU.f16x2 ops): the
+// epilogue of the K = 768 fc1 GEMM has ~0.2 cycles per element per SM before it, not the MMAs, bounds the
+// kernel, and the fp32 erf form costs ~25 issue slots per element. Phi(z) is evaluated in its tanh form,
+// 0.5 (1 + tanh(sqrt(2/pi) (z + 0.044715 z^3))), |error| < 5e-4 against the erf form, i.e. below the
+// resolution of the bf16 values it produces (the fp32 validation path uses exact erff); gelu'(z) =
+// Phi(z) + z phi(z) with phi from ex2.approx.
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ void gelu_fast2(float z0, float z1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
   const __half2 z = __floats2half2_rn(z0, z1);
-  const __half2 a = __hmul2(__habs2(z), __float2half2_rn(0.70710678f));
-  const __half2 t = h2rcp(__hfma2(__float2half2_rn(0.3275911f), a, __float2half2_rn(1.f)));
-  const __half2 e = h2exp(__hmul2(__hmul2(z, z), __float2half2_rn(-0.5f)));
-  __half2 poly = __hfma2(t, __float2half2_rn(1.061405429f), __float2half2_rn(-1.453152027f));
-  poly = __hfma2(poly, t, __float2half2_rn(1.421413741f));
-  poly = __hfma2(poly, t, __float2half2_rn(-0.284496736f));
-  poly = __hfma2(poly, t, __float2half2_rn(0.254829592f));
-  const __half2 erf_abs = __hfma2(__hneg2(__hmul2(poly, t)), e, __float2half2_rn(1.f));
-  // copysign(erf_abs, z): move z's sign bits over
-  const uint32_t zs = *reinterpret_cast<const uint32_t*>(&z) & 0x80008000u;
-  const uint32_t es = (*reinterpret_cast<const uint32_t*>(&erf_abs) & 0x7fff7fffu) | zs;
-  const __half2 cdf = __hfma2(__float2half2_rn(0.5f), *reinterpret_cast<const __half2*>(&es), __float2half2_rn(0.5f));
+  const __half2 z2 = __hmul2(z, z);
+  const __half2 inner = __hmul2(z, __hfma2(z2, __float2half2_rn(0.0356774081f), __float2half2_rn(0.7978845608f)));
+  uint32_t th, ex;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2_as_u32(inner)));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(ex) : "r"(h2_as_u32(__hmul2(z2, __float2half2_rn(-0.7213475204f)))));  // exp(-z^2/2)
+  const __half2 cdf = __hfma2(u32_as_h2(th), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
   const __half2 g = __hmul2(z, cdf);
-  const __half2 dg = __hfma2(__hmul2(z, e), __float2half2_rn(0.39894228f), cdf);
+  const __half2 dg = __hfma2(__hmul2(z, u32_as_h2(ex)), __float2half2_rn(0.3989422804f), cdf);
   const float2 gf = __half22float2(g), dgf = __half22float2(dg);
   g_bf16x2 = pack_bf16(gf.x, gf.y);
   dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
@@ -182,6 +181,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
         const WorkItem w = decode_item(p, item);
         const int m0 = w.m_tile * PAIR_M + cta_rank * CTA_M;
         const int n0 = w.n_tile * BLOCK_N + cta_rank * (BLOCK_N / 2);
+        // Epilogue operand (gelu' / residual) of this CTA's slab: pulled into L2 by bulk prefetches spread over
+        // the item's k-blocks, one main loop ahead of the epilogue warps that read it with plain loads (they
+        // then see L2 instead of HBM latency).
+        constexpr bool kPrefetch = EPI == MOME_EPI_DGELU || EPI == MOME_EPI_RESIDUAL;
+        const GemmGroupDev& gp = p.g[w.g];
+        const int pf_esz = EPI == MOME_EPI_DGELU ? 2 : 4;
+        const long long pf_ld = EPI == MOME_EPI_DGELU ? p.ldaux : p.ldres;
+        const char* pf_base = (EPI == MOME_EPI_DGELU ? static_cast<const char*>(gp.aux) : reinterpret_cast<const char*>(gp.res)) +
+                              (static_cast<long long>(m0) * pf_ld + static_cast<long long>(w.n_tile) * BLOCK_N) * pf_esz;
+        const int pf_bytes = min(BLOCK_N, p.N - w.n_tile * BLOCK_N) * pf_esz;
+        const int pf_rows = kPrefetch ? min(CTA_M, gp.M - m0) : 0;
+        const int pf_per_kb = (pf_rows + (w.kb1 - w.kb0) - 1) / max(1, w.kb1 - w.kb0);
+        int pf_next = 0;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -200,6 +212,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 128; ++j)
               tma_load_2d_pair(b_dst + j * kAtomBytes, &p.tma_b[w.g], &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+          }
+          if (kPrefetch) {
+            const int pf_end = min(pf_rows, pf_next + pf_per_kb);
+            for (; pf_next < pf_end; ++pf_next) l2_prefetch(pf_base + pf_next * pf_ld * pf_esz, pf_bytes);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }

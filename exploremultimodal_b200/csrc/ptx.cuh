@@ -74,6 +74,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// bulk prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address into L2
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
