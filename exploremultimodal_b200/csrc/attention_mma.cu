@@ -57,6 +57,23 @@ __device__ __forceinline__ void load_tile_async(uint8_t* tile, const __nv_bfloat
   }
 }
 
+// Two tiles over the same 64 sequence rows in one pass (K and V of qkv; or Q of qkv and dO): a thread always
+// copies 16-byte chunk (tid & 7) of rows (tid >> 3) + 16 i, so the row -> packed-buffer mapping is evaluated
+// once per row and the swizzled destination offset is a per-thread constant.
+__device__ __forceinline__ void load_tile_pair_async(uint8_t* tile_a, const __nv_bfloat16* ga, long long lda, uint8_t* tile_b,
+                                                     const __nv_bfloat16* gb, long long ldb, const Seq& sd, int n, int t0) {
+  const int r0 = threadIdx.x >> 3, ch = threadIdx.x & 7;
+  const uint32_t dst = r0 * 128 + ((ch ^ (r0 & 7)) << 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + r0 + 16 * i;
+    const bool valid = t < n;
+    const long long row = seq_row(sd, valid ? t : 0);
+    cp_async_16(tile_a + dst + i * 2048, ga + row * lda + ch * 8, valid);
+    cp_async_16(tile_b + dst + i * 2048, gb + row * ldb + ch * 8, valid);
+  }
+}
+
 // A fragments (4 k-steps) of the warp's 16 rows [r0, r0 + 16) of a swizzled tile
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], uint32_t tile, int r0) {
   const int lane = threadIdx.x & 31;
@@ -182,8 +199,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
 
   auto load_stage = [&](int tile) {
     const int slot = tile % kFwdStages;
-    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
-    load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
+    load_tile_pair_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, ring + (2 * slot + 1) * kTileBytes,
+                         qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
     load_keep(keep + slot * kKeepBytes, key_mask, sd, n, tile * kT);
   };
   load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
@@ -300,12 +317,11 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
 
   auto load_stage = [&](int tile) {
     const int slot = tile % kBwdStages;
-    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, sd, n, tile * kT);
-    load_tile_async(ring + (2 * slot + 1) * kTileBytes, qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
+    load_tile_pair_async(ring + (2 * slot) * kTileBytes, qkv + d + h * kT, ld, ring + (2 * slot + 1) * kTileBytes,
+                         qkv + 2 * d + h * kT, ld, sd, n, tile * kT);
     load_keep(keep + slot * kKeepBytes, key_mask, sd, n, tile * kT);
   };
-  load_tile_async(Qs, qkv + h * kT, ld, sd, n, q0);
-  load_tile_async(Gs, dout + h * kT, static_cast<long long>(d), sd, n, q0);
+  load_tile_pair_async(Qs, qkv + h * kT, ld, Gs, dout + h * kT, static_cast<long long>(d), sd, n, q0);
 #pragma unroll
   for (int i = 0; i < kBwdStages; ++i) {
     if (i < ntiles) load_stage(i);
@@ -422,16 +438,15 @@ __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __n
 
   auto load_stage = [&](int tile) {
     const int slot = tile % kBwdStages;
-    load_tile_async(ring + (2 * slot) * kTileBytes, qkv + h * kT, ld, sd, n, tile * kT);
-    load_tile_async(ring + (2 * slot + 1) * kTileBytes, dout + h * kT, static_cast<long long>(d), sd, n, tile * kT);
+    load_tile_pair_async(ring + (2 * slot) * kTileBytes, qkv + h * kT, ld, ring + (2 * slot + 1) * kTileBytes, dout + h * kT,
+                         static_cast<long long>(d), sd, n, tile * kT);
     if (threadIdx.x < kT) {
       const int i = tile * kT + threadIdx.x;
       lse_s[slot * kT + threadIdx.x] = i < n ? lse[stat0 + i] * kLog2e : INFINITY;  // +inf => p = 0 for absent queries
       delta_s[slot * kT + threadIdx.x] = i < n ? delta_ws[stat0 + i] : 0.f;
     }
   };
-  load_tile_async(Ks, qkv + d + h * kT, ld, sd, n, k0);
-  load_tile_async(Vs, qkv + 2 * d + h * kT, ld, sd, n, k0);
+  load_tile_pair_async(Ks, qkv + d + h * kT, ld, Vs, qkv + 2 * d + h * kT, ld, sd, n, k0);
 #pragma unroll
   for (int i = 0; i < kBwdStages; ++i) {
     if (i < ntiles) load_stage(i);
