@@ -150,6 +150,17 @@ class ClockSampler:
                 'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def gemm_traffic(args):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over
+    all gemm_pair_kernel launches of one step) from the committed ncu capture of this same workload
+    (profiles/r01_gemm_traffic.json, made by profiles/summarize_launches.py); None for other workloads."""
+    path = os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')
+    if args.model != 'vlmo_base' or args.batch != 128 or args.precision != 'bf16' or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get('dram_bytes_per_launch')
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -349,12 +360,12 @@ def run_mome(args):
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
         'gpu_launches': int(launches_per_step * args.steps),
         'gpu_launches_per_step': int(launches_per_step),
-        'roofline': {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel (grouped tcgen05/TMEM GEMM, all launches)',
+        'roofline': {'bound': 'tensor', 'kernel': 'gemm_pair_kernel (grouped tcgen05/TMEM GEMM, CTA pairs; all launches)',
                      'achieved': gemm_tflops, 'peak': sustained, 'unit': 'TFLOP/s',
                      'frac': gemm_tflops / sustained, 'frac_of_burst_peak': gemm_tflops / burst, 'peak_source': peak_src,
                      'launches': int(n_l.value), 'kernel_ms_per_step': ms_g.value / prof_steps,
-                     'kernel_share_of_step': ms_g.value / prof_steps / eager_ms_step,
-                     'eager_ms_per_step': eager_ms_step, 'traffic': None},
+                     'kernel_share_of_step': ms_g.value / prof_steps / ms_step,
+                     'eager_ms_per_step': eager_ms_step, 'traffic': gemm_traffic(args)},
         'clocks': clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
