@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 K_MAJOR, MN_MAJOR = 0, 1
 MAX_GROUPS = 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmGroup(C.Structure):
@@ -31,6 +31,29 @@ class GemmArgs(C.Structure):
                 ('lda', C.c_int64), ('ldb', C.c_int64), ('ldo', C.c_int64), ('ldo2', C.c_int64),
                 ('ldres', C.c_int64), ('ldaux', C.c_int64), ('gamma', C.c_void_p),
                 ('group', GemmGroup * MAX_GROUPS)]
+
+
+class BlockGroup(C.Structure):
+    _fields_ = [('first_row', C.c_int64), ('rows', C.c_int64), ('w1', C.c_void_p), ('b1', C.c_void_p),
+                ('w2', C.c_void_p), ('b2', C.c_void_p), ('dw1', C.c_void_p), ('db1', C.c_void_p),
+                ('dw2', C.c_void_p), ('db2', C.c_void_p), ('colsum_part', C.c_void_p)]
+
+
+class BlockArgs(C.Structure):
+    """MomeBlockArgs of include/mome.h (field order is the ABI)."""
+    _fields_ = ([('dtype', C.c_int32), ('num_heads', C.c_int32), ('num_groups', C.c_int32), ('num_seqs', C.c_int32),
+                 ('max_seq_len', C.c_int32), ('reserved', C.c_int32), ('tokens', C.c_int64), ('d', C.c_int64),
+                 ('hid', C.c_int64), ('eps', C.c_float), ('scale', C.c_float), ('seq_desc', C.c_void_p),
+                 ('key_mask', C.c_void_p)]
+                + [(n, C.c_void_p) for n in ('gamma_1', 'gamma_2', 'n1w', 'n1b', 'n2w', 'n2b', 'qkv_bias', 'proj_b',
+                                             'w_qkv', 'w_proj')]
+                + [('group', BlockGroup * MAX_GROUPS)]
+                + [(n, C.c_void_p) for n in ('x', 'h', 'mean1', 'rstd1', 'qkv', 'o', 'lse', 'br1', 'x1', 'h2', 'mean2',
+                                             'rstd2', 'gp', 'u', 'br2', 'x2', 'dx2', 'dx', 'dgamma_1', 'dgamma_2',
+                                             'dn1w', 'dn1b', 'dn2w', 'dn2b', 'dqkv_bias', 'dproj_b', 'dw_qkv',
+                                             'dw_proj', 's_dbr2', 's_dh2', 's_dbr1', 's_do', 's_dh', 's_dz', 's_dqkv',
+                                             's_dx1', 's_delta', 'ws')]
+                + [('ws_bytes', C.c_size_t)])
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -55,6 +78,8 @@ _SIGNATURES = {
     'mome_itc_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mome_itc_fwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'mome_itc_bwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'mome_block_fwd': (C.c_int, [C.POINTER(BlockArgs), _P]),
+    'mome_block_bwd': (C.c_int, [C.POINTER(BlockArgs), _P]),
     'mome_prof_enable': (C.c_int, [C.c_int]),
     'mome_prof_read': (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
     'mome_launch_count': (C.c_int64, []),

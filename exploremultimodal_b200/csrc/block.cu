@@ -1,0 +1,133 @@
+// One MoME block per call: native sequencing of the kernels of Block.forward (reference vlmo.py:187-197)
+// and of its backward. No computation of its own — it exists so that the host pays one FFI call per block
+// and direction instead of ~20 (the Python host was launch-bound in eager mode without it).
+#include "common.cuh"
+
+namespace {
+
+inline size_t esize(int dtype) { return dtype == MOME_BF16 ? 2 : 4; }
+inline const char* at(const void* p, int64_t row, int64_t ld, size_t es) { return static_cast<const char*>(p) + row * ld * es; }
+inline char* at(void* p, int64_t row, int64_t ld, size_t es) { return static_cast<char*>(p) + row * ld * es; }
+
+MomeGemmArgs gemm_args(int dtype, int a_major, int b_major, int epilogue, int out_dtype, int groups, int64_t N, int64_t lda,
+                       int64_t ldb, int64_t ldo) {
+  MomeGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.dtype = dtype; g.a_major = a_major; g.b_major = b_major; g.epilogue = epilogue; g.out_dtype = out_dtype;
+  g.num_groups = groups; g.N = N; g.lda = lda; g.ldb = ldb; g.ldo = ldo;
+  return g;
+}
+
+#define MOME_TRY(call)          \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != MOME_OK) return rc_; \
+  } while (0)
+
+}  // namespace
+
+extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
+  MOME_REQUIRE(a != nullptr && a->num_groups >= 1 && a->num_groups <= MOME_MAX_GROUPS, "block_fwd: bad group count");
+  const int dt = a->dtype;
+  const size_t es = esize(dt);
+  const int64_t T = a->tokens, d = a->d, hid = a->hid;
+  if (T == 0) return MOME_OK;
+  MOME_TRY(mome_ln_fwd(a->x, a->n1w, a->n1b, a->h, dt, a->mean1, a->rstd1, T, d, a->eps, stream));
+  {
+    MomeGemmArgs g = gemm_args(dt, 0, 0, MOME_EPI_STORE, dt, 1, 3 * d, d, d, 3 * d);
+    g.group[0].a = a->h; g.group[0].b = a->w_qkv; g.group[0].M = T; g.group[0].K = d; g.group[0].out = a->qkv;
+    g.group[0].bias = a->qkv_bias;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  MOME_TRY(mome_attn_fwd(a->qkv, dt, a->seq_desc, a->key_mask, a->o, a->lse, T, a->num_seqs, a->max_seq_len, a->num_heads, a->scale, stream));
+  {
+    MomeGemmArgs g = gemm_args(dt, 0, 0, MOME_EPI_RESIDUAL, MOME_F32, 1, d, d, d, d);
+    g.ldo2 = d; g.ldres = d; g.gamma = a->gamma_1;
+    g.group[0].a = a->o; g.group[0].b = a->w_proj; g.group[0].M = T; g.group[0].K = d; g.group[0].out = a->x1;
+    g.group[0].out2 = a->br1; g.group[0].bias = a->proj_b; g.group[0].res = a->x;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  MOME_TRY(mome_ln_fwd(a->x1, a->n2w, a->n2b, a->h2, dt, a->mean2, a->rstd2, T, d, a->eps, stream));
+  {
+    MomeGemmArgs g1 = gemm_args(dt, 0, 0, MOME_EPI_GELU, dt, a->num_groups, hid, d, d, hid);
+    g1.ldo2 = hid;
+    MomeGemmArgs g2 = gemm_args(dt, 0, 0, MOME_EPI_RESIDUAL, MOME_F32, a->num_groups, d, hid, hid, d);
+    g2.ldo2 = d; g2.ldres = d; g2.gamma = a->gamma_2;
+    for (int i = 0; i < a->num_groups; ++i) {
+      const MomeBlockGroup& s = a->group[i];
+      g1.group[i].a = at(a->h2, s.first_row, d, es); g1.group[i].b = s.w1; g1.group[i].M = s.rows; g1.group[i].K = d;
+      g1.group[i].out = at(a->u, s.first_row, hid, es); g1.group[i].out2 = at(a->gp, s.first_row, hid, es); g1.group[i].bias = s.b1;
+      g2.group[i].a = at(a->u, s.first_row, hid, es); g2.group[i].b = s.w2; g2.group[i].M = s.rows; g2.group[i].K = hid;
+      g2.group[i].out = at(a->x2, s.first_row, d, 4); g2.group[i].out2 = at(a->br2, s.first_row, d, es); g2.group[i].bias = s.b2;
+      g2.group[i].res = reinterpret_cast<const float*>(at(a->x1, s.first_row, d, 4));
+    }
+    MOME_TRY(mome_gemm(&g1, stream));
+    MOME_TRY(mome_gemm(&g2, stream));
+  }
+  return MOME_OK;
+}
+
+extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
+  MOME_REQUIRE(a != nullptr && a->num_groups >= 1 && a->num_groups <= MOME_MAX_GROUPS, "block_bwd: bad group count");
+  const int dt = a->dtype;
+  const size_t es = esize(dt);
+  const int64_t T = a->tokens, d = a->d, hid = a->hid;
+  if (T == 0) return MOME_OK;
+  // ---- expert FFN branch: x2 = x1 + gamma_2 * fc2(gelu(fc1(LN2(x1))))
+  MomeGemmArgs dgrad2 = gemm_args(dt, 0, 1, MOME_EPI_DGELU, dt, a->num_groups, hid, d, hid, hid);
+  dgrad2.ldaux = hid;
+  MomeGemmArgs wgrad2 = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, a->num_groups, hid, d, hid, hid);
+  MomeGemmArgs wgrad1 = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, a->num_groups, d, hid, d, d);
+  MomeGemmArgs dgrad1 = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, a->num_groups, d, hid, d, d);
+  for (int i = 0; i < a->num_groups; ++i) {
+    const MomeBlockGroup& s = a->group[i];
+    MOME_TRY(mome_scale_bwd(reinterpret_cast<const float*>(at(a->dx2, s.first_row, d, 4)), at(a->br2, s.first_row, d, es), dt, a->gamma_2,
+                            at(a->s_dbr2, s.first_row, d, es), dt, a->dgamma_2, s.db2, s.rows, d, a->ws, a->ws_bytes, stream));
+    dgrad2.group[i].a = at(a->s_dbr2, s.first_row, d, es); dgrad2.group[i].b = s.w2; dgrad2.group[i].M = s.rows; dgrad2.group[i].K = d;
+    dgrad2.group[i].out = at(a->s_dz, s.first_row, hid, es); dgrad2.group[i].aux = at(a->gp, s.first_row, hid, es);
+    dgrad2.group[i].colsum = s.colsum_part;
+    wgrad2.group[i].a = at(a->s_dbr2, s.first_row, d, es); wgrad2.group[i].b = at(a->u, s.first_row, hid, es); wgrad2.group[i].M = d;
+    wgrad2.group[i].K = s.rows; wgrad2.group[i].out = s.dw2;
+    wgrad1.group[i].a = at(a->s_dz, s.first_row, hid, es); wgrad1.group[i].b = at(a->h2, s.first_row, d, es); wgrad1.group[i].M = hid;
+    wgrad1.group[i].K = s.rows; wgrad1.group[i].out = s.dw1;
+    dgrad1.group[i].a = at(a->s_dz, s.first_row, hid, es); dgrad1.group[i].b = s.w1; dgrad1.group[i].M = s.rows; dgrad1.group[i].K = hid;
+    dgrad1.group[i].out = at(a->s_dh2, s.first_row, d, es);
+  }
+  MOME_TRY(mome_gemm(&dgrad2, stream));  // dz = (dbr2 W2) * gelu'(z); per-32-row column sums -> colsum_part
+  for (int i = 0; i < a->num_groups; ++i) {
+    const MomeBlockGroup& s = a->group[i];
+    MOME_TRY(mome_colreduce(s.colsum_part, (s.rows + 31) / 32, hid, s.db1, stream));
+  }
+  MOME_TRY(mome_gemm(&wgrad2, stream));  // dW2 += dbr2^T u
+  MOME_TRY(mome_gemm(&wgrad1, stream));  // dW1 += dz^T h2
+  MOME_TRY(mome_gemm(&dgrad1, stream));  // dh2 = dz W1
+  // LN2 backward (+ dx2) fused with the LayerScale backward of the attention branch
+  MOME_TRY(mome_ln_bwd_scale(a->s_dh2, dt, a->x1, a->mean2, a->rstd2, a->n2w, a->dx2, a->s_dx1, a->dn2w, a->dn2b, a->br1, a->gamma_1,
+                             a->s_dbr1, a->dgamma_1, a->dproj_b, T, d, a->ws, a->ws_bytes, stream));
+  // ---- attention branch: x1 = x + gamma_1 * proj(attn(qkv(LN1(x))))
+  {
+    MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, d, d, d);
+    g.group[0].a = a->s_dbr1; g.group[0].b = a->o; g.group[0].M = d; g.group[0].K = T; g.group[0].out = a->dw_proj;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  {
+    MomeGemmArgs g = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, 1, d, d, d, d);
+    g.group[0].a = a->s_dbr1; g.group[0].b = a->w_proj; g.group[0].M = T; g.group[0].K = d; g.group[0].out = a->s_do;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  MOME_TRY(mome_attn_bwd(a->qkv, a->o, a->s_do, dt, a->seq_desc, a->key_mask, a->lse, a->s_dqkv, a->s_delta, T, a->num_seqs,
+                         a->max_seq_len, a->num_heads, a->scale, stream));
+  if (a->dqkv_bias != nullptr)
+    MOME_TRY(mome_colsum(a->s_dqkv, dt, T, 3 * d, 3 * d, a->dqkv_bias, a->ws, a->ws_bytes, stream));
+  {
+    MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, 3 * d, d, d);
+    g.group[0].a = a->s_dqkv; g.group[0].b = a->h; g.group[0].M = 3 * d; g.group[0].K = T; g.group[0].out = a->dw_qkv;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  {
+    MomeGemmArgs g = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, 1, d, 3 * d, d, d);
+    g.group[0].a = a->s_dqkv; g.group[0].b = a->w_qkv; g.group[0].M = T; g.group[0].K = 3 * d; g.group[0].out = a->s_dh;
+    MOME_TRY(mome_gemm(&g, stream));
+  }
+  return mome_ln_bwd(a->s_dh, dt, a->x, a->mean1, a->rstd1, a->n1w, a->s_dx1, a->dx, a->dn1w, a->dn1b, T, d, a->ws, a->ws_bytes, stream);
+}

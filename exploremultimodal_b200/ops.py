@@ -184,133 +184,115 @@ class BlockParams:
                  'w_qkv', 'w_proj', 'proj_b', 'experts')
 
 
+def _fill_common(a, lay, key_mask, p, x, hid):
+    tokens, d = x.shape
+    a.dtype, a.num_heads, a.num_groups = p.code, p.num_heads, len(lay.groups)
+    a.num_seqs, a.max_seq_len = lay.num_seqs, lay.max_seq_len
+    a.tokens, a.d, a.hid = tokens, d, hid
+    a.eps, a.scale = p.eps, (d // p.num_heads) ** -0.5
+    a.seq_desc, a.key_mask = lay.seq_desc.data_ptr(), L.ptr(key_mask)
+    a.gamma_1, a.gamma_2 = L.ptr(p.gamma_1), L.ptr(p.gamma_2)
+    a.n1w, a.n1b, a.n2w, a.n2b = p.n1w.data_ptr(), p.n1b.data_ptr(), p.n2w.data_ptr(), p.n2b.data_ptr()
+    a.qkv_bias, a.proj_b = L.ptr(p.qkv_bias), p.proj_b.data_ptr()
+    a.w_qkv, a.w_proj = p.w_qkv.data_ptr(), p.w_proj.data_ptr()
+    for i, (s, n, route) in enumerate(lay.groups):
+        w1, b1, w2, b2 = p.experts[route][:4]
+        g = a.group[i]
+        g.first_row, g.rows = s, n
+        g.w1, g.b1, g.w2, g.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+
+
+def _fill_saved(a, saved):
+    (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2) = saved
+    a.x, a.h, a.mean1, a.rstd1 = x.data_ptr(), h.data_ptr(), mean1.data_ptr(), rstd1.data_ptr()
+    a.qkv, a.o, a.lse, a.br1, a.x1 = qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), br1.data_ptr(), x1.data_ptr()
+    a.h2, a.mean2, a.rstd2 = h2.data_ptr(), mean2.data_ptr(), rstd2.data_ptr()
+    a.gp, a.u, a.br2 = gp.data_ptr(), u.data_ptr(), br2.data_ptr()
+
+
 def block_forward(x, lay, key_mask, p):
-    """x fp32 [tokens, d] -> (x_out fp32, saved tensors). Mirrors reference vlmo.py:187-197."""
-    code = p.code
-    es = _esize(code)
+    """x fp32 [tokens, d] -> (x_out fp32, saved tensors). Mirrors reference vlmo.py:187-197; the kernel
+    sequence (LN, QKV GEMM, attention, proj GEMM + LayerScale + residual, LN, fc1 GEMM + GELU, fc2 GEMM +
+    LayerScale + residual) is issued by ONE native call, mome_block_fwd."""
     tokens, d = x.shape
     dev = x.device
-    cdt = _tdtype(code)
+    cdt = _tdtype(p.code)
     hid = p.experts[lay.groups[0][2]][0].shape[0]
-    scale = (d // p.num_heads) ** -0.5
-
-    h, mean1, rstd1 = ln_fwd(x, p.n1w, p.n1b, code, p.eps)
-    qkv = torch.empty(tokens, 3 * d, dtype=cdt, device=dev)
-    gemm(code, L.K_MAJOR, L.K_MAJOR, L.EPI_STORE, code, 3 * d, d, d, 3 * d,
-         [dict(a=h.data_ptr(), b=p.w_qkv.data_ptr(), M=tokens, K=d, out=qkv.data_ptr(), bias=L.ptr(p.qkv_bias))])
-    o, lse = attn_fwd(qkv, lay, key_mask, p.num_heads, scale)
-    x1 = torch.empty_like(x)
-    br1 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    gemm(code, L.K_MAJOR, L.K_MAJOR, L.EPI_RESIDUAL, L.F32, d, d, d, d,
-         [dict(a=o.data_ptr(), b=p.w_proj.data_ptr(), M=tokens, K=d, out=x1.data_ptr(), out2=br1.data_ptr(),
-               bias=p.proj_b.data_ptr(), res=x.data_ptr())],
-         ldo2=d, ldres=d, gamma=L.ptr(p.gamma_1))
-
-    h2, mean2, rstd2 = ln_fwd(x1, p.n2w, p.n2b, code, p.eps)
-    z = torch.empty(tokens, hid, dtype=cdt, device=dev)
-    u = torch.empty(tokens, hid, dtype=cdt, device=dev)
-    x2 = torch.empty_like(x)
-    br2 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    g1, g2 = [], []
-    for (s, n, route) in lay.groups:
-        w1, b1, w2, b2 = p.experts[route][:4]
-        g1.append(dict(a=h2.data_ptr() + s * d * es, b=w1.data_ptr(), M=n, K=d, out=u.data_ptr() + s * hid * es,
-                       out2=z.data_ptr() + s * hid * es, bias=b1.data_ptr()))
-        g2.append(dict(a=u.data_ptr() + s * hid * es, b=w2.data_ptr(), M=n, K=hid, out=x2.data_ptr() + s * d * 4,
-                       out2=br2.data_ptr() + s * d * es, bias=b2.data_ptr(), res=x1.data_ptr() + s * d * 4))
-    gemm(code, L.K_MAJOR, L.K_MAJOR, L.EPI_GELU, code, hid, d, d, hid, g1, ldo2=hid)
-    gemm(code, L.K_MAJOR, L.K_MAJOR, L.EPI_RESIDUAL, L.F32, d, hid, hid, d, g2, ldo2=d, ldres=d, gamma=L.ptr(p.gamma_2))
-    saved = (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, z, u, br2)
+    f32 = dict(dtype=torch.float32, device=dev)
+    act = dict(dtype=cdt, device=dev)
+    h, h2 = torch.empty(tokens, d, **act), torch.empty(tokens, d, **act)
+    o, br1, br2 = torch.empty(tokens, d, **act), torch.empty(tokens, d, **act), torch.empty(tokens, d, **act)
+    qkv = torch.empty(tokens, 3 * d, **act)
+    gp, u = torch.empty(tokens, hid, **act), torch.empty(tokens, hid, **act)
+    stats = torch.empty(4, tokens, **f32)
+    mean1, rstd1, mean2, rstd2 = stats[0], stats[1], stats[2], stats[3]
+    lse = torch.empty(lay.num_seqs * p.num_heads * lay.max_seq_len, **f32)
+    x1, x2 = torch.empty_like(x), torch.empty_like(x)
+    saved = (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2)
+    a = L.BlockArgs()
+    _fill_common(a, lay, key_mask, p, x, hid)
+    _fill_saved(a, saved)
+    a.x2 = x2.data_ptr()
+    L.check(L.lib().mome_block_fwd(C.byref(a), L.stream()), 'mome_block_fwd')
     return x2, saved
 
 
 def block_backward(dx2, lay, key_mask, p, saved, targets=None):
-    """Returns (dx, grads) where grads maps parameter slots to fp32 gradient tensors.
+    """Returns (dx, grads) where grads maps parameter slots to fp32 gradient tensors; one native call,
+    mome_block_bwd, issues the 14 kernels.
 
     Every parameter-gradient kernel accumulates (+=). `targets` maps a slot to an existing fp32 buffer
     (the parameter's .grad) to accumulate into directly; slots without a target get a fresh zeroed
     buffer that autograd then adds to .grad."""
     targets = targets or {}
+    x = saved[0]
+    gp = saved[12]
+    tokens, d = x.shape
+    hid = gp.shape[1]
+    dev = x.device
+    cdt = _tdtype(p.code)
+    f32 = dict(dtype=torch.float32, device=dev)
+    act = dict(dtype=cdt, device=dev)
 
     def buf(slot, *shape):
         t = targets.get(slot)
         return t if t is not None else torch.zeros(*shape, **f32)
-    (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, z, u, br2) = saved
-    code = p.code
-    es = _esize(code)
-    cdt = _tdtype(code)
-    tokens, d = x.shape
-    dev = x.device
-    hid = z.shape[1]
-    scale = (d // p.num_heads) ** -0.5
-    f32 = dict(dtype=torch.float32, device=dev)
+
     dx2 = dx2.contiguous()
-    grads = {}
-
-    # ---- expert FFN branch: x2 = x1 + gamma_2 * (fc2(gelu(fc1(LN2(x1)))))
     has_gamma = p.gamma_1 is not None
-    dgamma2 = buf('gamma_2', d) if has_gamma else None
-    dbr2 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    dz = torch.empty(tokens, hid, dtype=cdt, device=dev)
-    dh2 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    g_dgrad2, g_wgrad2, g_wgrad1, g_dgrad1, parts = [], [], [], [], []
-    for (s, n, route) in lay.groups:
-        w1, b1, w2, b2 = p.experts[route][:4]
-        db2 = buf(('mlp', route, 3), d)
-        db1 = buf(('mlp', route, 1), hid)
-        dw2 = buf(('mlp', route, 2), d, hid)
-        dw1 = buf(('mlp', route, 0), hid, d)
+    grads = {}
+    a = L.BlockArgs()
+    _fill_common(a, lay, key_mask, p, x, hid)
+    _fill_saved(a, saved)
+    keep = []  # scratch tensors must outlive the (asynchronous) call: the caching allocator is stream ordered
+    for i, (s, n, route) in enumerate(lay.groups):
+        dw1, db1 = buf(('mlp', route, 0), hid, d), buf(('mlp', route, 1), hid)
+        dw2, db2 = buf(('mlp', route, 2), d, hid), buf(('mlp', route, 3), d)
+        part = torch.zeros((n + 31) // 32, hid, **f32)
         grads[('mlp', route)] = (dw1, db1, dw2, db2)
-        scale_bwd(dx2, br2, p.gamma_2, dbr2, dgamma2, db2, s, n)
-        part = torch.zeros((n + 31) // 32, hid, **f32)  # per-32-row column sums of dz, written by the DGELU epilogue
-        parts.append((part, db1))
-        g_dgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=w2.data_ptr(), M=n, K=d, out=dz.data_ptr() + s * hid * es,
-                             aux=z.data_ptr() + s * hid * es, colsum=part.data_ptr()))
-        g_wgrad2.append(dict(a=dbr2.data_ptr() + s * d * es, b=u.data_ptr() + s * hid * es, M=d, K=n, out=dw2.data_ptr()))
-        g_wgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=h2.data_ptr() + s * d * es, M=hid, K=n, out=dw1.data_ptr()))
-        g_dgrad1.append(dict(a=dz.data_ptr() + s * hid * es, b=w1.data_ptr(), M=n, K=hid, out=dh2.data_ptr() + s * d * es))
-    # dz = (dbr2 @ W2) * gelu'(z); `z` holds gelu'(z), stashed by the forward GELU epilogue; db1 += colsum(dz)
-    gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_DGELU, code, hid, d, hid, hid, g_dgrad2, ldaux=hid)
-    for part, db1 in parts:
-        colreduce(part, db1)
-    # dW2 += dbr2^T @ u
-    gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, hid, d, hid, hid, g_wgrad2)
-    # dW1 += dz^T @ h2 ; dh2 = dz @ W1
-    gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, hid, d, d, g_wgrad1)
-    gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, hid, d, d, g_dgrad1)
-    # LN2 backward (+ residual gradient dx2) fused with the LayerScale backward of the attention branch:
-    # dx1, then dbr1 = gamma_1 * dx1, dgamma_1 += dx1 * br1, dproj_b += dbr1 while dx1 is still in registers
-    dn2w, dn2b = buf('n2w', d), buf('n2b', d)
+        g = a.group[i]
+        g.dw1, g.db1, g.dw2, g.db2, g.colsum_part = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), part.data_ptr()
+        keep.append(part)
     dgamma1 = buf('gamma_1', d) if has_gamma else None
-    dproj_b = buf('proj_b', d)
-    dbr1 = torch.empty(tokens, d, dtype=cdt, device=dev)
-    dx1 = torch.empty_like(x1)
+    dgamma2 = buf('gamma_2', d) if has_gamma else None
+    dn1w, dn1b, dn2w, dn2b = buf('n1w', d), buf('n1b', d), buf('n2w', d), buf('n2b', d)
+    dproj_b, dw_proj, dw_qkv = buf('proj_b', d), buf('w_proj', d, d), buf('w_qkv', 3 * d, d)
+    dqkv_bias = torch.zeros(3 * d, **f32) if p.qkv_bias is not None else None  # [dq_bias | unused k part | dv_bias]
+    dx = torch.empty_like(x)
+    a.dx2, a.dx = dx2.data_ptr(), dx.data_ptr()
+    a.dgamma_1, a.dgamma_2 = L.ptr(dgamma1), L.ptr(dgamma2)
+    a.dn1w, a.dn1b, a.dn2w, a.dn2b = dn1w.data_ptr(), dn1b.data_ptr(), dn2w.data_ptr(), dn2b.data_ptr()
+    a.dqkv_bias, a.dproj_b, a.dw_qkv, a.dw_proj = L.ptr(dqkv_bias), dproj_b.data_ptr(), dw_qkv.data_ptr(), dw_proj.data_ptr()
+    s_d = torch.empty(5, tokens, d, **act)       # dbr2, dh2, dbr1, do, dh
+    s_dz = torch.empty(tokens, hid, **act)
+    s_dqkv = torch.empty(tokens, 3 * d, **act)
+    s_dx1 = torch.empty_like(x)
+    s_delta = torch.empty_like(saved[6])
+    a.s_dbr2, a.s_dh2, a.s_dbr1, a.s_do, a.s_dh = (s_d[i].data_ptr() for i in range(5))
+    a.s_dz, a.s_dqkv, a.s_dx1, a.s_delta = s_dz.data_ptr(), s_dqkv.data_ptr(), s_dx1.data_ptr(), s_delta.data_ptr()
     ws = reduce_ws(dev)
-    L.check(L.lib().mome_ln_bwd_scale(dh2.data_ptr(), code, x1.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(),
-                                      p.n2w.data_ptr(), dx2.data_ptr(), dx1.data_ptr(), dn2w.data_ptr(), dn2b.data_ptr(),
-                                      br1.data_ptr(), L.ptr(p.gamma_1), dbr1.data_ptr(), L.ptr(dgamma1),
-                                      dproj_b.data_ptr(), tokens, d, ws.data_ptr(), ws.numel(), L.stream()),
-            'mome_ln_bwd_scale')
-    dw_proj = buf('w_proj', d, d)
-    gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, d, d, d,
-         [dict(a=dbr1.data_ptr(), b=o.data_ptr(), M=d, K=tokens, out=dw_proj.data_ptr())])
-    do = torch.empty(tokens, d, dtype=cdt, device=dev)
-    gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, d, d, d,
-         [dict(a=dbr1.data_ptr(), b=p.w_proj.data_ptr(), M=tokens, K=d, out=do.data_ptr())])
-    dqkv = attn_bwd(qkv, o, do, lay, key_mask, lse, p.num_heads, scale)
-    dqkv_bias = None
-    if p.qkv_bias is not None:
-        dqkv_bias = torch.zeros(3 * d, **f32)  # [dq_bias | (unused k part) | dv_bias]: split by the caller
-        colsum(dqkv, dqkv_bias)
-    dw_qkv = buf('w_qkv', 3 * d, d)
-    gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, d, 3 * d, d, d,
-         [dict(a=dqkv.data_ptr(), b=h.data_ptr(), M=3 * d, K=tokens, out=dw_qkv.data_ptr())])
-    dh = torch.empty(tokens, d, dtype=cdt, device=dev)
-    gemm(code, L.K_MAJOR, L.MN_MAJOR, L.EPI_STORE, code, d, 3 * d, d, d,
-         [dict(a=dqkv.data_ptr(), b=p.w_qkv.data_ptr(), M=tokens, K=3 * d, out=dh.data_ptr())])
-    dn1w, dn1b = buf('n1w', d), buf('n1b', d)
-    dx = ln_bwd(dh, x, mean1, rstd1, p.n1w, dx1, dn1w, dn1b)
-
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+    L.check(L.lib().mome_block_bwd(C.byref(a), L.stream()), 'mome_block_bwd')
     grads.update(gamma_1=dgamma1, gamma_2=dgamma2, n1w=dn1w, n1b=dn1b, n2w=dn2w, n2b=dn2b, qkv_bias=dqkv_bias,
                  w_qkv=dw_qkv, w_proj=dw_proj, proj_b=dproj_b)
     return dx, grads

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MOME_ABI_VERSION 3
+#define MOME_ABI_VERSION 4
 #define MOME_MAX_GROUPS 4
 
 enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
@@ -167,6 +167,60 @@ int mome_itc_fwd_peer(const float* i_feat, const float* t_feat, const void* peer
 int mome_itc_bwd_peer(const float* i_feat, const float* t_feat, const void* peers, const float* temp, int32_t bs,
                       int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat,
                       float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream);
+
+/* ---- One whole MoME block per call ------------------------------------------------------------------
+ * reference: Block.forward, vlmo.py:187-197, and its autograd backward. These two entry points only
+ * sequence the kernels above (7 launches forward, 14 backward) in native code, so that a host language
+ * with expensive FFI calls (Python: ~20 ctypes calls + as many tensor allocations per block otherwise)
+ * issues one call per block and direction. All buffers are caller-owned; shapes: tokens x d unless noted.
+ *
+ * forward : x -> LN1 -> qkv GEMM -> attention -> proj GEMM (+gamma_1, residual) = x1
+ *             -> LN2 -> fc1 GEMM (+GELU, per expert group) -> fc2 GEMM (+gamma_2, residual) = x2
+ * backward: dx2 -> ... -> dx; every parameter gradient is ACCUMULATED (+=) into the given fp32 buffer. */
+typedef struct {
+  int64_t first_row, rows;   /* expert segment of the packed token buffer */
+  const void* w1;            /* fc1.weight [hid, d]  (compute dtype) */
+  const float* b1;           /* fc1.bias   [hid] */
+  const void* w2;            /* fc2.weight [d, hid]  (compute dtype) */
+  const float* b2;           /* fc2.bias   [d] */
+  float *dw1, *db1, *dw2, *db2; /* backward: gradient accumulators */
+  float* colsum_part;        /* backward scratch: ZEROED fp32 [ceil(rows / 32), hid] */
+} MomeBlockGroup;
+
+typedef struct {
+  int32_t dtype;             /* MomeDtype of activations / weights fed to the GEMMs */
+  int32_t num_heads, num_groups, num_seqs, max_seq_len, reserved;
+  int64_t tokens, d, hid;
+  float eps, scale;          /* LayerNorm eps; attention scale (head_dim^-0.5) */
+  const int32_t* seq_desc;   /* [num_seqs, 4] (see mome_attn_fwd) */
+  const uint8_t* key_mask;   /* [tokens] or NULL */
+  /* parameters (fp32) and compute-dtype weights */
+  const float *gamma_1, *gamma_2, *n1w, *n1b, *n2w, *n2b, *qkv_bias /* [3d] = [q_bias, 0, v_bias] or NULL */, *proj_b;
+  const void *w_qkv /* [3d, d] */, *w_proj /* [d, d] */;
+  MomeBlockGroup group[MOME_MAX_GROUPS];
+  /* activations: written by the forward, read by the backward */
+  const float* x;            /* block input (fp32 residual stream) */
+  void* h;  float* mean1; float* rstd1;   /* LN1 output (compute dtype) and statistics [tokens] */
+  void* qkv;                 /* [tokens, 3d] */
+  void* o;  float* lse;      /* attention output; log-sum-exp [num_seqs * num_heads * max_seq_len] */
+  void* br1; float* x1;      /* proj output before LayerScale; residual stream after the attention branch */
+  void* h2; float* mean2; float* rstd2;
+  void* gp; void* u;         /* gelu'(z) and gelu(z), [tokens, hid] */
+  void* br2; float* x2;      /* fc2 output before LayerScale; block output */
+  /* backward only */
+  const float* dx2;          /* gradient of the block output */
+  float* dx;                 /* gradient of the block input */
+  float *dgamma_1, *dgamma_2, *dn1w, *dn1b, *dn2w, *dn2b, *dqkv_bias /* [3d] */, *dproj_b, *dw_qkv, *dw_proj;
+  void *s_dbr2, *s_dh2, *s_dbr1, *s_do, *s_dh;  /* scratch [tokens, d] (compute dtype) */
+  void* s_dz;                /* scratch [tokens, hid] */
+  void* s_dqkv;              /* scratch [tokens, 3d] */
+  float* s_dx1;              /* scratch fp32 [tokens, d] */
+  float* s_delta;            /* scratch fp32, same size as lse */
+  void* ws; size_t ws_bytes; /* mome_reduce_ws_bytes(max(hid, 3d)) */
+} MomeBlockArgs;
+
+int mome_block_fwd(const MomeBlockArgs* args, void* stream);
+int mome_block_bwd(const MomeBlockArgs* args, void* stream);
 
 /* ---- measurement hooks (bench.py): CUDA-event timing of every mome_gemm launch on its own stream */
 int mome_prof_enable(int on);
