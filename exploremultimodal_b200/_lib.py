@@ -15,13 +15,13 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 K_MAJOR, MN_MAJOR = 0, 1
 MAX_GROUPS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class GemmGroup(C.Structure):
     _fields_ = [('a', C.c_void_p), ('b', C.c_void_p), ('M', C.c_int64), ('K', C.c_int64),
                 ('out', C.c_void_p), ('out2', C.c_void_p), ('bias', C.c_void_p), ('res', C.c_void_p),
-                ('aux', C.c_void_p), ('colsum', C.c_void_p)]
+                ('aux', C.c_void_p), ('row0', C.c_int64), ('colsum', C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -30,7 +30,13 @@ class GemmArgs(C.Structure):
                 ('split_k', C.c_int32), ('reserved', C.c_int32), ('N', C.c_int64),
                 ('lda', C.c_int64), ('ldb', C.c_int64), ('ldo', C.c_int64), ('ldo2', C.c_int64),
                 ('ldres', C.c_int64), ('ldaux', C.c_int64), ('gamma', C.c_void_p),
-                ('group', GemmGroup * MAX_GROUPS)]
+                ('group', GemmGroup * MAX_GROUPS), ('drop_seed', C.c_void_p), ('row_scale', C.c_void_p),
+                ('drop_salt', C.c_uint32), ('drop_p', C.c_float)]
+
+
+class Dropout(C.Structure):
+    """MomeDropout of include/mome.h."""
+    _fields_ = [('seed', C.c_void_p), ('row_scale', C.c_void_p), ('row0', C.c_int64), ('salt', C.c_uint32), ('p', C.c_float)]
 
 
 class BlockGroup(C.Structure):
@@ -53,7 +59,9 @@ class BlockArgs(C.Structure):
                                              'dn1w', 'dn1b', 'dn2w', 'dn2b', 'dqkv_bias', 'dproj_b', 'dw_qkv',
                                              'dw_proj', 's_dbr2', 's_dh2', 's_dbr1', 's_do', 's_dh', 's_dz', 's_dqkv',
                                              's_dx1', 's_delta', 'ws')]
-                + [('ws_bytes', C.c_size_t)])
+                + [('ws_bytes', C.c_size_t), ('drop_seed', C.c_void_p), ('row_sample', C.c_void_p),
+                   ('row_scale1', C.c_void_p), ('row_scale2', C.c_void_p), ('drop_salt', C.c_uint32),
+                   ('p_attn', C.c_float), ('p_hidden', C.c_float), ('p_branch', C.c_float), ('p_path', C.c_float)])
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -63,15 +71,16 @@ _SIGNATURES = {
     'mome_sm_count': (C.c_int, []),
     'mome_ln_fwd': (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _L, _L, _F, _P]),
     'mome_ln_bwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, C.c_size_t, _P]),
-    'mome_ln_bwd_scale': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, C.c_size_t, _P]),
-    'mome_scale_bwd': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _L, _L, _P, C.c_size_t, _P]),
+    'mome_ln_bwd_scale': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, C.c_size_t, _P]),
+    'mome_scale_bwd': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _L, _L, _P, _P, C.c_size_t, _P]),
+    'mome_droppath_scales': (C.c_int, [_P, _L, _P, C.c_uint32, _F, _P, _P]),
     'mome_colsum': (C.c_int, [_P, C.c_int, _L, _L, _L, _P, _P, C.c_size_t, _P]),
     'mome_colreduce': (C.c_int, [_P, _L, _L, _P, _P]),
     'mome_reduce_ws_bytes': (C.c_size_t, [_L]),
     'mome_cast_bf16': (C.c_int, [_P, _P, _L, _P]),
     'mome_gemm': (C.c_int, [C.POINTER(GemmArgs), _P]),
-    'mome_attn_fwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
-    'mome_attn_bwd': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
+    'mome_attn_fwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, C.c_uint32, _F, _P]),
+    'mome_attn_bwd': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, C.c_uint32, _F, _P]),
     'mome_l2norm_fwd': (C.c_int, [_P, C.c_int, _P, _P, _L, _L, _P]),
     'mome_l2norm_bwd': (C.c_int, [_P, _P, _P, _P, _L, _L, _P]),
     'mome_itc_fwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

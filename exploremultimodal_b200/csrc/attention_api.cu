@@ -11,10 +11,10 @@ int attn_bwd_simt_dispatch(const void* qkv, const void* out, const void* dout, i
                            const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len,
                            int H, float scale, cudaStream_t stream);
 int attn_fwd_mma(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse, int num_seqs,
-                 int max_seq_len, int H, float scale, cudaStream_t stream);
+                 int max_seq_len, int H, float scale, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, cudaStream_t stream);
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask,
                  const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len, int H, float scale,
-                 cudaStream_t stream);
+                 const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, cudaStream_t stream);
 
 // MOME_ATTN_SIMT=1 forces the CUDA-core kernels for bf16 too (cross-check in tests / debugging).
 static bool force_simt() {
@@ -29,24 +29,31 @@ static bool force_simt() {
 using namespace mome;
 
 extern "C" int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse,
-                             int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, void* stream) {
+                             int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale,
+                             const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream) {
+  const bool drop = drop_seed != nullptr && drop_p > 0.f;
+  MOME_REQUIRE(!drop || (dtype == MOME_BF16 && !force_simt()), "attn_fwd: dropout exists on the bf16 tensor-core path only");
   MOME_REQUIRE(dtype == MOME_F32 || dtype == MOME_BF16, "attn_fwd: unknown dtype %d", dtype);
   MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_fwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
   if (num_seqs == 0 || tokens == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MOME_BF16 && !force_simt())
-    return attn_fwd_mma(qkv, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, s);
+    return attn_fwd_mma(qkv, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, drop_seed, drop_salt, drop_p, s);
   return attn_fwd_simt_dispatch(qkv, dtype, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, s);
 }
 
 extern "C" int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
                              const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens, int32_t num_seqs,
-                             int32_t max_seq_len, int32_t num_heads, float scale, void* stream) {
+                             int32_t max_seq_len, int32_t num_heads, float scale, const uint32_t* drop_seed, uint32_t drop_salt,
+                             float drop_p, void* stream) {
+  const bool drop = drop_seed != nullptr && drop_p > 0.f;
+  MOME_REQUIRE(!drop || (dtype == MOME_BF16 && !force_simt()), "attn_bwd: dropout exists on the bf16 tensor-core path only");
   MOME_REQUIRE(dtype == MOME_F32 || dtype == MOME_BF16, "attn_bwd: unknown dtype %d", dtype);
   MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_bwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
   if (num_seqs == 0 || tokens == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MOME_BF16 && !force_simt())
-    return attn_bwd_mma(qkv, out, dout, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, num_heads, scale, s);
+    return attn_bwd_mma(qkv, out, dout, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, num_heads, scale, drop_seed,
+                        drop_salt, drop_p, s);
   return attn_bwd_simt_dispatch(qkv, out, dout, dtype, seq_desc, key_mask, lse, dqkv, delta_ws, num_seqs, max_seq_len, num_heads, scale, s);
 }

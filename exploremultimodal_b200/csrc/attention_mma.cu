@@ -16,6 +16,7 @@
 // Replaces: reference vlmo.py:79-95 and its autograd backward. The tcgen05 variant is future work:
 // at N <= 237 the whole (sequence, head) problem is 4 tiles and the kernel is latency bound.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "ptx.cuh"
 #include "vec.cuh"
 
@@ -173,6 +174,21 @@ __device__ __forceinline__ void load_keep(uint8_t* keep, const uint8_t* key_mask
 }
 __device__ __forceinline__ bool tile_all_kept(const uint8_t* keep) { return keep[kT] != 0 && keep[kT + 1] != 0; }
 
+// ---- dropout on the attention probabilities (reference vlmo.py:93). One 32-bit mask word per (sequence, head,
+// query, pair of adjacent keys): low half-word -> even key, high half-word -> odd key (csrc/dropout.cuh).
+struct AttnDrop {
+  const uint32_t* seed;
+  uint32_t salt, thr;
+};
+__device__ __forceinline__ uint32_t attn_drop_row(int s, int H, int h, int max_seq_len, int i) {
+  return ((static_cast<uint32_t>(s) * H + h) * max_seq_len + i) * static_cast<uint32_t>((max_seq_len + 1) >> 1);
+}
+// a: even key, b: odd key of the pair the word belongs to
+__device__ __forceinline__ void attn_drop_pair(uint32_t word, uint32_t thr, float scale, float& a, float& b) {
+  a = (word & 255u) >= thr ? a * scale : 0.f;
+  b = ((word >> 16) & 255u) >= thr ? b * scale : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------- forward
 // The streamed side lives in a ring of kFwdStages (K, V) tile pairs, one cp.async group per tile.
 // Measured (profiles/): the kernel is bound by issue slots / occupancy, not by load latency, so the ring
@@ -181,9 +197,11 @@ constexpr int kFwdStages = 2;
 // smem: Q | kFwdStages x (K, V) tiles, keep[kFwdStages][64]
 constexpr int kFwdSmem = (1 + 2 * kFwdStages) * kTileBytes + kFwdStages * kKeepBytes;
 
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seq_desc,
                                                                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out,
-                                                                float* __restrict__ lse, int H, int max_seq_len, float scale) {
+                                                                float* __restrict__ lse, int H, int max_seq_len, float scale,
+                                                                const AttnDrop ad) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Qs = smem;
   uint8_t* ring = smem + kTileBytes;  // stage s: K at ring + 2 s kTileBytes, V right after
@@ -215,6 +233,9 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
   zero_acc(o);
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const float sl2 = scale * kLog2e;
+  const uint32_t dkey = DROP ? drop_mix(ad.salt, __ldg(ad.seed)) : 0u;
+  const float dscale = drop_scale(ad.thr);
+  const uint32_t drow0 = attn_drop_row(s, H, h, max_seq_len, q0 + warp * 16 + g), drow1 = attn_drop_row(s, H, h, max_seq_len, q0 + warp * 16 + g + 8);
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int slot = kt % kFwdStages;
@@ -269,6 +290,14 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
     for (int nt = 0; nt < 8; ++nt) {
       o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
     }
+    if (DROP) {  // the normaliser l keeps the undropped probabilities; only what multiplies V is dropped
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t jp = kt * 32 + nt * 4 + t;
+        attn_drop_pair(drop_mix(drow0 + jp, dkey), ad.thr, dscale, sacc[nt][0], sacc[nt][1]);
+        attn_drop_pair(drop_mix(drow1 + jp, dkey), ad.thr, dscale, sacc[nt][2], sacc[nt][3]);
+      }
+    }
     uint32_t pf[4][4];
     acc_to_a(pf, sacc);
     warp_gemm<true>(o, pf, smem_u32(ring + (2 * slot + 1) * kTileBytes));
@@ -294,11 +323,12 @@ constexpr int kBwdStages = 3;
 // smem: Q | dO | kBwdStages x (K, V) tiles, keep[kBwdStages][64], delta[64] floats
 constexpr int kDqSmem = (2 + 2 * kBwdStages) * kTileBytes + kBwdStages * kKeepBytes + kT * 4;
 
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                                                                    const __nv_bfloat16* __restrict__ dout, const int32_t* __restrict__ seq_desc,
                                                                    const uint8_t* __restrict__ key_mask, const float* __restrict__ lse,
                                                                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ delta_ws, int H,
-                                                                   int max_seq_len, float scale) {
+                                                                   int max_seq_len, float scale, const AttnDrop ad) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Qs = smem;
   uint8_t* Gs = smem + kTileBytes;
@@ -362,6 +392,9 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
   const float sl2 = scale * kLog2e;
   float dq[8][4];
   zero_acc(dq);
+  const uint32_t dkey = DROP ? drop_mix(ad.salt, __ldg(ad.seed)) : 0u;
+  const float dscale = drop_scale(ad.thr);
+  const uint32_t drow0 = attn_drop_row(s, H, h, max_seq_len, r0), drow1 = attn_drop_row(s, H, h, max_seq_len, r1);
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int slot = kt % kBwdStages;
@@ -378,6 +411,14 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
     zero_acc(dp);
     warp_gemm<false>(sacc, qf, smem_u32(ring + (2 * slot) * kTileBytes));
     warp_gemm<false>(dp, gf, smem_u32(ring + (2 * slot + 1) * kTileBytes));
+    if (DROP) {  // dP of a dropped probability is zero, of a kept one it carries the 1 / (1 - p) scale
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t jp = kt * 32 + nt * 4 + t;
+        attn_drop_pair(drop_mix(drow0 + jp, dkey), ad.thr, dscale, dp[nt][0], dp[nt][1]);
+        attn_drop_pair(drop_mix(drow1 + jp, dkey), ad.thr, dscale, dp[nt][2], dp[nt][3]);
+      }
+    }
     const uint8_t* kp = keep + slot * kKeepBytes;
     if (tile_all_kept(kp)) {
 #pragma unroll
@@ -416,10 +457,12 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma_kernel(const __nv_bf
 // smem: K | V | kBwdStages x (Q, dO) tiles, lse[kBwdStages][64], delta[kBwdStages][64] floats
 constexpr int kDkvSmem = (2 + 2 * kBwdStages) * kTileBytes + 2 * kBwdStages * kT * 4;
 
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                                                                     const int32_t* __restrict__ seq_desc, const uint8_t* __restrict__ key_mask,
                                                                     const float* __restrict__ lse, const float* __restrict__ delta_ws,
-                                                                    __nv_bfloat16* __restrict__ dqkv, int H, int max_seq_len, float scale) {
+                                                                    __nv_bfloat16* __restrict__ dqkv, int H, int max_seq_len, float scale,
+                                                                    const AttnDrop ad) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Ks = smem;
   uint8_t* Vs = smem + kTileBytes;
@@ -462,6 +505,10 @@ __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __n
   float dk[8][4], dv[8][4];
   zero_acc(dk);
   zero_acc(dv);
+  const uint32_t dkey = DROP ? drop_mix(ad.salt, __ldg(ad.seed)) : 0u;
+  const float dscale = drop_scale(ad.thr);
+  const uint32_t dsh0 = (j0 & 1) * 16, dsh1 = (j1 & 1) * 16;   // which half-word of the mask word belongs to this thread's keys
+  const uint32_t kp2 = static_cast<uint32_t>((max_seq_len + 1) >> 1);
 
   for (int qt = 0; qt < ntiles; ++qt) {
     const int slot = qt % kBwdStages;
@@ -492,7 +539,33 @@ __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __n
       }
       acc_to_a(pf, st);
     }
-    warp_gemm<true>(dv, pf, g_tile);
+    if (DROP) {
+      // P^T stays undropped in pf (it is the factor of dS^T); a dropped element is flagged in the sign bit of its
+      // bf16 value (probabilities are >= 0), and a dropped + scaled copy feeds dV += drop(P)^T dO.
+      uint32_t pd[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int nt = 2 * j + h2;
+          const uint32_t qa = qt * kT + nt * 8 + 2 * t;  // this thread's two queries: qa, qa + 1
+          const uint32_t ra = attn_drop_row(s, H, h, max_seq_len, qa), rb = ra + kp2;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {  // r = 0: key row j0 (pf[j][2 h2]), r = 1: key row j1 (pf[j][2 h2 + 1])
+            const uint32_t jj = r == 0 ? j0 : j1, sh = r == 0 ? dsh0 : dsh1;
+            const bool ka = ((drop_mix(ra + (jj >> 1), dkey) >> sh) & 255u) >= ad.thr;
+            const bool kb = ((drop_mix(rb + (jj >> 1), dkey) >> sh) & 255u) >= ad.thr;
+            uint32_t& w = pf[j][2 * h2 + r];
+            const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            pd[j][2 * h2 + r] = pack_bf16(ka ? pv.x * dscale : 0.f, kb ? pv.y * dscale : 0.f);
+            w |= (ka ? 0u : 0x8000u) | (kb ? 0u : 0x80000000u);
+          }
+        }
+      }
+      warp_gemm<true>(dv, pd, g_tile);
+    } else {
+      warp_gemm<true>(dv, pf, g_tile);
+    }
     {
       float dpt[8][4];
       zero_acc(dpt);
@@ -504,8 +577,16 @@ __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __n
         for (int h2 = 0; h2 < 2; ++h2) {
           const int nt = 2 * j + h2, c = nt * 8 + 2 * t;
           const float Da = Dq[c], Db = Dq[c + 1];
-          const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pf[j][2 * h2]));
-          const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pf[j][2 * h2 + 1]));
+          const uint32_t w0 = pf[j][2 * h2], w1 = pf[j][2 * h2 + 1];
+          const uint32_t a0 = w0 & 0x7fff7fffu, a1 = w1 & 0x7fff7fffu;
+          const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a0));
+          const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a1));
+          if (DROP) {  // dP^T of dropped probabilities is zero, kept ones carry the scale
+            dpt[nt][0] = (w0 & 0x8000u) ? 0.f : dpt[nt][0] * dscale;
+            dpt[nt][1] = (w0 & 0x80000000u) ? 0.f : dpt[nt][1] * dscale;
+            dpt[nt][2] = (w1 & 0x8000u) ? 0.f : dpt[nt][2] * dscale;
+            dpt[nt][3] = (w1 & 0x80000000u) ? 0.f : dpt[nt][3] * dscale;
+          }
           dpt[nt][0] = p0.x * (dpt[nt][0] - Da);
           dpt[nt][1] = p0.y * (dpt[nt][1] - Db);
           dpt[nt][2] = p1.x * (dpt[nt][2] - Da);
@@ -539,39 +620,53 @@ int opt_in(K kern, int bytes, const char* what) {
 }  // namespace
 
 int attn_fwd_mma(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse, int num_seqs,
-                 int max_seq_len, int H, float scale, cudaStream_t stream) {
+                 int max_seq_len, int H, float scale, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in(attn_fwd_mma_kernel, kFwdSmem, "attn_fwd_mma");
+    int rc = opt_in(attn_fwd_mma_kernel<false>, kFwdSmem, "attn_fwd_mma");
+    if (rc == MOME_OK) rc = opt_in(attn_fwd_mma_kernel<true>, kFwdSmem, "attn_fwd_mma");
     if (rc != MOME_OK) return rc;
     configured = true;
   }
   dim3 grid((max_seq_len + kT - 1) / kT, H, num_seqs);
-  attn_fwd_mma_kernel<<<grid, kThreads, kFwdSmem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), seq_desc, key_mask,
-                                                            static_cast<__nv_bfloat16*>(out), lse, H, max_seq_len, scale);
+  const AttnDrop ad{drop_seed, drop_salt, drop_threshold(drop_p)};
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  if (drop_seed != nullptr && drop_p > 0.f)
+    attn_fwd_mma_kernel<true><<<grid, kThreads, kFwdSmem, stream>>>(q, seq_desc, key_mask, static_cast<__nv_bfloat16*>(out), lse, H, max_seq_len, scale, ad);
+  else
+    attn_fwd_mma_kernel<false><<<grid, kThreads, kFwdSmem, stream>>>(q, seq_desc, key_mask, static_cast<__nv_bfloat16*>(out), lse, H, max_seq_len, scale, ad);
   return check_launch("attn_fwd_mma");
 }
 
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask,
                  const float* lse, void* dqkv, float* delta_ws, int num_seqs, int max_seq_len, int H, float scale,
-                 cudaStream_t stream) {
+                 const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in(attn_bwd_dq_mma_kernel, kDqSmem, "attn_bwd_dq_mma");
-    if (rc != MOME_OK) return rc;
-    rc = opt_in(attn_bwd_dkv_mma_kernel, kDkvSmem, "attn_bwd_dkv_mma");
+    int rc = opt_in(attn_bwd_dq_mma_kernel<false>, kDqSmem, "attn_bwd_dq_mma");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_dq_mma_kernel<true>, kDqSmem, "attn_bwd_dq_mma");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_dkv_mma_kernel<false>, kDkvSmem, "attn_bwd_dkv_mma");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_dkv_mma_kernel<true>, kDkvSmem, "attn_bwd_dkv_mma");
     if (rc != MOME_OK) return rc;
     configured = true;
   }
   dim3 grid((max_seq_len + kT - 1) / kT, H, num_seqs);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(dout);
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
-  attn_bwd_dq_mma_kernel<<<grid, kThreads, kDqSmem, stream>>>(q, static_cast<const __nv_bfloat16*>(out), go, seq_desc, key_mask, lse, dq,
-                                                              delta_ws, H, max_seq_len, scale);
+  const AttnDrop ad{drop_seed, drop_salt, drop_threshold(drop_p)};
+  const bool drop = drop_seed != nullptr && drop_p > 0.f;
+  if (drop)
+    attn_bwd_dq_mma_kernel<true><<<grid, kThreads, kDqSmem, stream>>>(q, o, go, seq_desc, key_mask, lse, dq, delta_ws, H, max_seq_len, scale, ad);
+  else
+    attn_bwd_dq_mma_kernel<false><<<grid, kThreads, kDqSmem, stream>>>(q, o, go, seq_desc, key_mask, lse, dq, delta_ws, H, max_seq_len, scale, ad);
   int rc = check_launch("attn_bwd_dq_mma");
   if (rc != MOME_OK) return rc;
-  attn_bwd_dkv_mma_kernel<<<grid, kThreads, kDkvSmem, stream>>>(q, go, seq_desc, key_mask, lse, delta_ws, dq, H, max_seq_len, scale);
+  if (drop)
+    attn_bwd_dkv_mma_kernel<true><<<grid, kThreads, kDkvSmem, stream>>>(q, go, seq_desc, key_mask, lse, delta_ws, dq, H, max_seq_len, scale, ad);
+  else
+    attn_bwd_dkv_mma_kernel<false><<<grid, kThreads, kDkvSmem, stream>>>(q, go, seq_desc, key_mask, lse, delta_ws, dq, H, max_seq_len, scale, ad);
   return check_launch("attn_bwd_dkv_mma");
 }
 

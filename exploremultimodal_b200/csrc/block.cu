@@ -18,6 +18,9 @@ MomeGemmArgs gemm_args(int dtype, int a_major, int b_major, int epilogue, int ou
   return g;
 }
 
+// dropout is active for probability p?
+inline bool on(const MomeBlockArgs* a, float p) { return a->drop_seed != nullptr && p > 0.f; }
+
 #define MOME_TRY(call)          \
   do {                          \
     int rc_ = (call);           \
@@ -32,6 +35,14 @@ extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
   const size_t es = esize(dt);
   const int64_t T = a->tokens, d = a->d, hid = a->hid;
   if (T == 0) return MOME_OK;
+  MOME_REQUIRE(dt == MOME_BF16 || !(on(a, a->p_attn) || on(a, a->p_hidden) || on(a, a->p_branch) || on(a, a->p_path)),
+               "block_fwd: dropout exists on the bf16 path only");
+  const bool path = on(a, a->p_path);
+  if (path) {
+    MOME_REQUIRE(a->row_sample != nullptr && a->row_scale1 != nullptr && a->row_scale2 != nullptr, "block_fwd: stochastic depth needs row_sample / row_scale buffers");
+    MOME_TRY(mome_droppath_scales(a->row_sample, T, a->drop_seed, a->drop_salt + 4, a->p_path, a->row_scale1, stream));
+    MOME_TRY(mome_droppath_scales(a->row_sample, T, a->drop_seed, a->drop_salt + 5, a->p_path, a->row_scale2, stream));
+  }
   MOME_TRY(mome_ln_fwd(a->x, a->n1w, a->n1b, a->h, dt, a->mean1, a->rstd1, T, d, a->eps, stream));
   {
     MomeGemmArgs g = gemm_args(dt, 0, 0, MOME_EPI_STORE, dt, 1, 3 * d, d, d, 3 * d);
@@ -39,12 +50,15 @@ extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
     g.group[0].bias = a->qkv_bias;
     MOME_TRY(mome_gemm(&g, stream));
   }
-  MOME_TRY(mome_attn_fwd(a->qkv, dt, a->seq_desc, a->key_mask, a->o, a->lse, T, a->num_seqs, a->max_seq_len, a->num_heads, a->scale, stream));
+  MOME_TRY(mome_attn_fwd(a->qkv, dt, a->seq_desc, a->key_mask, a->o, a->lse, T, a->num_seqs, a->max_seq_len, a->num_heads, a->scale,
+                         on(a, a->p_attn) ? a->drop_seed : nullptr, a->drop_salt, a->p_attn, stream));
   {
     MomeGemmArgs g = gemm_args(dt, 0, 0, MOME_EPI_RESIDUAL, MOME_F32, 1, d, d, d, d);
     g.ldo2 = d; g.ldres = d; g.gamma = a->gamma_1;
     g.group[0].a = a->o; g.group[0].b = a->w_proj; g.group[0].M = T; g.group[0].K = d; g.group[0].out = a->x1;
     g.group[0].out2 = a->br1; g.group[0].bias = a->proj_b; g.group[0].res = a->x;
+    if (on(a, a->p_branch)) { g.drop_seed = a->drop_seed; g.drop_salt = a->drop_salt + 1; g.drop_p = a->p_branch; }
+    if (path) g.row_scale = a->row_scale1;
     MOME_TRY(mome_gemm(&g, stream));
   }
   MOME_TRY(mome_ln_fwd(a->x1, a->n2w, a->n2b, a->h2, dt, a->mean2, a->rstd2, T, d, a->eps, stream));
@@ -53,8 +67,13 @@ extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
     g1.ldo2 = hid;
     MomeGemmArgs g2 = gemm_args(dt, 0, 0, MOME_EPI_RESIDUAL, MOME_F32, a->num_groups, d, hid, hid, d);
     g2.ldo2 = d; g2.ldres = d; g2.gamma = a->gamma_2;
+    if (on(a, a->p_hidden)) { g1.drop_seed = a->drop_seed; g1.drop_salt = a->drop_salt + 2; g1.drop_p = a->p_hidden; }
+    if (on(a, a->p_branch)) { g2.drop_seed = a->drop_seed; g2.drop_salt = a->drop_salt + 3; g2.drop_p = a->p_branch; }
+    if (path) g2.row_scale = a->row_scale2;
     for (int i = 0; i < a->num_groups; ++i) {
       const MomeBlockGroup& s = a->group[i];
+      g1.group[i].row0 = s.first_row;
+      g2.group[i].row0 = s.first_row;
       g1.group[i].a = at(a->h2, s.first_row, d, es); g1.group[i].b = s.w1; g1.group[i].M = s.rows; g1.group[i].K = d;
       g1.group[i].out = at(a->u, s.first_row, hid, es); g1.group[i].out2 = at(a->gp, s.first_row, hid, es); g1.group[i].bias = s.b1;
       g2.group[i].a = at(a->u, s.first_row, hid, es); g2.group[i].b = s.w2; g2.group[i].M = s.rows; g2.group[i].K = hid;
@@ -73,6 +92,7 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   const size_t es = esize(dt);
   const int64_t T = a->tokens, d = a->d, hid = a->hid;
   if (T == 0) return MOME_OK;
+  const bool path = on(a, a->p_path);
   // ---- expert FFN branch: x2 = x1 + gamma_2 * fc2(gelu(fc1(LN2(x1))))
   MomeGemmArgs dgrad2 = gemm_args(dt, 0, 1, MOME_EPI_DGELU, dt, a->num_groups, hid, d, hid, hid);
   dgrad2.ldaux = hid;
@@ -81,8 +101,9 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   MomeGemmArgs dgrad1 = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, a->num_groups, d, hid, d, d);
   for (int i = 0; i < a->num_groups; ++i) {
     const MomeBlockGroup& s = a->group[i];
+    const MomeDropout drop2{on(a, a->p_branch) ? a->drop_seed : nullptr, path ? a->row_scale2 : nullptr, s.first_row, a->drop_salt + 3, a->p_branch};
     MOME_TRY(mome_scale_bwd(reinterpret_cast<const float*>(at(a->dx2, s.first_row, d, 4)), at(a->br2, s.first_row, d, es), dt, a->gamma_2,
-                            at(a->s_dbr2, s.first_row, d, es), dt, a->dgamma_2, s.db2, s.rows, d, a->ws, a->ws_bytes, stream));
+                            at(a->s_dbr2, s.first_row, d, es), dt, a->dgamma_2, s.db2, s.rows, d, &drop2, a->ws, a->ws_bytes, stream));
     dgrad2.group[i].a = at(a->s_dbr2, s.first_row, d, es); dgrad2.group[i].b = s.w2; dgrad2.group[i].M = s.rows; dgrad2.group[i].K = d;
     dgrad2.group[i].out = at(a->s_dz, s.first_row, hid, es); dgrad2.group[i].aux = at(a->gp, s.first_row, hid, es);
     dgrad2.group[i].colsum = s.colsum_part;
@@ -102,8 +123,9 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   MOME_TRY(mome_gemm(&wgrad1, stream));  // dW1 += dz^T h2
   MOME_TRY(mome_gemm(&dgrad1, stream));  // dh2 = dz W1
   // LN2 backward (+ dx2) fused with the LayerScale backward of the attention branch
+  const MomeDropout drop1{on(a, a->p_branch) ? a->drop_seed : nullptr, path ? a->row_scale1 : nullptr, 0, a->drop_salt + 1, a->p_branch};
   MOME_TRY(mome_ln_bwd_scale(a->s_dh2, dt, a->x1, a->mean2, a->rstd2, a->n2w, a->dx2, a->s_dx1, a->dn2w, a->dn2b, a->br1, a->gamma_1,
-                             a->s_dbr1, a->dgamma_1, a->dproj_b, T, d, a->ws, a->ws_bytes, stream));
+                             a->s_dbr1, a->dgamma_1, a->dproj_b, T, d, &drop1, a->ws, a->ws_bytes, stream));
   // ---- attention branch: x1 = x + gamma_1 * proj(attn(qkv(LN1(x))))
   {
     MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, d, d, d);
@@ -116,7 +138,7 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
     MOME_TRY(mome_gemm(&g, stream));
   }
   MOME_TRY(mome_attn_bwd(a->qkv, a->o, a->s_do, dt, a->seq_desc, a->key_mask, a->lse, a->s_dqkv, a->s_delta, T, a->num_seqs,
-                         a->max_seq_len, a->num_heads, a->scale, stream));
+                         a->max_seq_len, a->num_heads, a->scale, on(a, a->p_attn) ? a->drop_seed : nullptr, a->drop_salt, a->p_attn, stream));
   if (a->dqkv_bias != nullptr)
     MOME_TRY(mome_colsum(a->s_dqkv, dt, T, 3 * d, 3 * d, a->dqkv_bias, a->ws, a->ws_bytes, stream));
   {

@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
 
 static int gemm_f32(const MomeGemmArgs* a, cudaStream_t stream) {
   MOME_REQUIRE(a->out_dtype == MOME_F32, "gemm(fp32): out must be fp32");
+  if ((a->drop_seed != nullptr && a->drop_p > 0.f) || a->row_scale != nullptr) {
+    set_error("gemm(fp32): dropout / stochastic depth exist on the bf16 path only");
+    return MOME_ERR_UNSUPPORTED;
+  }
   MOME_REQUIRE(a->num_groups >= 1 && a->num_groups <= MOME_MAX_GROUPS, "gemm: num_groups %d", a->num_groups);
   SimtParams p;
   memset(&p, 0, sizeof(p));

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dropout.cuh"
 #include "ptx.cuh"
 
 namespace mome {
@@ -49,6 +50,7 @@ struct GemmGroupDev {
   const float* res;
   const void* aux;
   float* colsum;
+  long long row0;
   int M;
   int k_blocks;
   int item_start;
@@ -60,6 +62,9 @@ struct alignas(64) GemmParams {
   CUtensorMap tma_b[MOME_MAX_GROUPS];
   GemmGroupDev g[MOME_MAX_GROUPS];
   const float* gamma;
+  const uint32_t* drop_seed;
+  const float* row_scale;
+  uint32_t drop_salt, drop_thr;
   long long ldo, ldo2, ldres, ldaux;
   int num_groups, total_items, n_tiles, splits;
   int N, epilogue, out_bf16, debug;
@@ -106,7 +111,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) { return __bfloat162
 // Phi(z) + z phi(z) with phi from ex2.approx.
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ void gelu_fast2(float z0, float z1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
+template <bool DROP>
+__device__ __forceinline__ void gelu_fast2(float z0, float z1, float m0, float m1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
   const __half2 z = __floats2half2_rn(z0, z1);
   const __half2 z2 = __hmul2(z, z);
   const __half2 inner = __hmul2(z, __hfma2(z2, __float2half2_rn(0.0356774081f), __float2half2_rn(0.7978845608f)));
@@ -116,7 +122,10 @@ __device__ __forceinline__ void gelu_fast2(float z0, float z1, uint32_t& g_bf16x
   const __half2 cdf = __hfma2(u32_as_h2(th), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
   const __half2 g = __hmul2(z, cdf);
   const __half2 dg = __hfma2(__hmul2(z, u32_as_h2(ex)), __float2half2_rn(0.3989422804f), cdf);
-  const float2 gf = __half22float2(g), dgf = __half22float2(dg);
+  float2 gf = __half22float2(g), dgf = __half22float2(dg);
+  if (DROP) {  // dropout after the activation (timm Mlp): both the value and the derivative carry mask * scale
+    gf.x *= m0; gf.y *= m1; dgf.x *= m0; dgf.y *= m1;
+  }
   g_bf16x2 = pack_bf16(gf.x, gf.y);
   dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
 }
@@ -132,7 +141,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DROP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -281,6 +290,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
       const long long out2_step = 4 * p.ldo2 * 2;
       const bool has_out2 = g.out2 != nullptr;
       const bool do_cs = (EPI == MOME_EPI_STORE || EPI == MOME_EPI_DGELU) && g.colsum != nullptr;
+      // dropout: one 32-bit mask word per lane-iteration (its 4 columns); group index advances by N / 4 * 4 rows = N per iteration
+      const uint32_t dkey = DROP ? drop_mix(p.drop_salt, __ldg(p.drop_seed)) : 0u;
+      const float dscale = drop_scale(p.drop_thr);
+      const uint32_t didx0 = drop_group(g.row0 + rfirst, p.N, col_base);
+      const float* rs_p = (EPI == MOME_EPI_RESIDUAL && p.row_scale != nullptr) ? p.row_scale + g.row0 + rfirst : nullptr;
 
       // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
       // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
@@ -353,15 +367,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
                 const uint32_t z01 = pack_bf16(v.x, v.y), z23 = pack_bf16(v.z, v.w);
                 const float2 za = unpack_bf16x2(z01), zb = unpack_bf16x2(z23);
                 uint2 u, du;
-                gelu_fast2(za.x, za.y, u.x, du.x);
-                gelu_fast2(zb.x, zb.y, u.y, du.y);
+                float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (DROP) dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
+                gelu_fast2<DROP>(za.x, za.y, dm.x, dm.y, u.x, du.x);
+                gelu_fast2<DROP>(zb.x, zb.y, dm.z, dm.w, u.y, du.y);
                 *reinterpret_cast<uint2*>(op) = u;
                 *reinterpret_cast<uint2*>(o2p) = du;
               } else if (EPI == MOME_EPI_RESIDUAL) {
                 // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
-                const uint2 bb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                uint2 bb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                if (DROP) {  // proj_drop / Mlp output dropout acts on the bf16 Linear output
+                  const float4 dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
+                  const float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y);
+                  bb = make_uint2(pack_bf16(t0.x * dm.x, t0.y * dm.y), pack_bf16(t1.x * dm.z, t1.y * dm.w));
+                }
                 if (has_out2) *reinterpret_cast<uint2*>(o2p) = bb;
-                const float2 ba = unpack_bf16x2(bb.x), bc = unpack_bf16x2(bb.y);
+                float2 ba = unpack_bf16x2(bb.x), bc = unpack_bf16x2(bb.y);
+                if (rs_p != nullptr) {  // stochastic depth: the whole branch of a dropped sample vanishes
+                  const float rsc = __ldg(rs_p + it * 4);
+                  ba.x *= rsc; ba.y *= rsc; bc.x *= rsc; bc.y *= rsc;
+                }
                 float4 rr = res[c % kResDepth][it];
                 rr.x = fmaf(gm4.x, ba.x, rr.x); rr.y = fmaf(gm4.y, ba.y, rr.y);
                 rr.z = fmaf(gm4.z, bc.x, rr.z); rr.w = fmaf(gm4.w, bc.y, rr.w);
@@ -476,11 +501,11 @@ std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DROP = false>
 int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = gemm_pair_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = gemm_pair_kernel<BLOCK_N, A_MN, B_MN, EPI, DROP>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -499,8 +524,12 @@ int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_
   if (!a_mn && !b_mn) {
     switch (p.epilogue) {
       case MOME_EPI_STORE: return launch_one<BLOCK_N, false, false, MOME_EPI_STORE>(p, grid, stream);
-      case MOME_EPI_GELU: return launch_one<BLOCK_N, false, false, MOME_EPI_GELU>(p, grid, stream);
-      case MOME_EPI_RESIDUAL: return launch_one<BLOCK_N, false, false, MOME_EPI_RESIDUAL>(p, grid, stream);
+      case MOME_EPI_GELU:
+        return p.drop_seed ? launch_one<BLOCK_N, false, false, MOME_EPI_GELU, true>(p, grid, stream)
+                           : launch_one<BLOCK_N, false, false, MOME_EPI_GELU>(p, grid, stream);
+      case MOME_EPI_RESIDUAL:
+        return p.drop_seed ? launch_one<BLOCK_N, false, false, MOME_EPI_RESIDUAL, true>(p, grid, stream)
+                           : launch_one<BLOCK_N, false, false, MOME_EPI_RESIDUAL>(p, grid, stream);
       case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, false, false, MOME_EPI_ATOMIC>(p, grid, stream);
     }
   } else if (!a_mn && b_mn) {
@@ -530,6 +559,9 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
   MOME_REQUIRE(a->epilogue != MOME_EPI_RESIDUAL || a->out_dtype == MOME_F32, "gemm: RESIDUAL epilogue needs fp32 out");
   MOME_REQUIRE((a->epilogue != MOME_EPI_GELU && a->epilogue != MOME_EPI_DGELU) || a->out_dtype == MOME_BF16,
                "gemm(bf16): GELU/DGELU epilogues write bf16");
+  MOME_REQUIRE(a->drop_seed == nullptr || a->drop_p <= 0.f || a->epilogue == MOME_EPI_GELU || a->epilogue == MOME_EPI_RESIDUAL,
+               "gemm: dropout is defined for the GELU and RESIDUAL epilogues only");
+  MOME_REQUIRE(a->row_scale == nullptr || a->epilogue == MOME_EPI_RESIDUAL, "gemm: row_scale needs the RESIDUAL epilogue");
   MOME_REQUIRE(a->ldo % 8 == 0 && a->ldo2 % 8 == 0 && a->ldres % 4 == 0 && a->ldaux % 8 == 0, "gemm: leading dims must keep rows 16-byte aligned");
 
   double flops = 0;
@@ -562,6 +594,10 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     p.out_bf16 = a->out_dtype == MOME_BF16;
     p.ldo = a->ldo; p.ldo2 = a->ldo2; p.ldres = a->ldres; p.ldaux = a->ldaux;
     p.gamma = a->gamma;
+    p.row_scale = a->row_scale;
+    p.drop_seed = (a->drop_seed != nullptr && a->drop_p > 0.f) ? a->drop_seed : nullptr;
+    p.drop_salt = a->drop_salt;
+    p.drop_thr = drop_threshold(a->drop_p);
     {
       static const int dbg = [] { const char* e = getenv("MOME_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
       p.debug = dbg;
@@ -597,7 +633,7 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
     for (int g = 0; g < a->num_groups && rc == MOME_OK; ++g) {
       const MomeGemmGroup& s = a->group[g];
       GemmGroupDev& d = p.g[g];
-      d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux; d.colsum = s.colsum;
+      d.out = s.out; d.out2 = s.out2; d.bias = s.bias; d.res = s.res; d.aux = s.aux; d.colsum = s.colsum; d.row0 = s.row0;
       d.M = static_cast<int>(s.M);
       d.k_blocks = static_cast<int>((s.K + BLOCK_K - 1) / BLOCK_K);
       d.item_start = item;

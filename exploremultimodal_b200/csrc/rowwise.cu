@@ -8,6 +8,7 @@
 // LayerScale multiply-adds (vlmo.py:194-196) and their autograd backward.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "dropout.cuh"
 #include "vec.cuh"
 
 namespace mome {
@@ -77,6 +78,24 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const float* __rest
 // sums over the row) are a block reduction batched over R rows per iteration. Few registers -> several
 // CTAs per SM and R x 3 independent 128-bit loads in flight per thread, which is what an HBM-bound
 // kernel needs.
+// device-side view of MomeDropout (include/mome.h)
+struct DropDev {
+  const uint32_t* seed;
+  const float* row_scale;
+  long long row0;
+  uint32_t salt, thr;
+};
+// mask * scale (and stochastic-depth multiplier) of the branch elements (row0 + r, c..c+3) of a d-wide matrix
+__device__ __forceinline__ float4 branch_mul4(const DropDev& dd, uint32_t key, float scale, long long r, int d, int c) {
+  float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (dd.seed != nullptr) m = drop_mul4(drop_group(dd.row0 + r, d, c), key, dd.thr, scale);
+  if (dd.row_scale != nullptr) {
+    const float rs = __ldg(dd.row_scale + dd.row0 + r);
+    m.x *= rs; m.y *= rs; m.z *= rs; m.w *= rs;
+  }
+  return m;
+}
+
 constexpr int kColRows = 4;   // rows per iteration (LayerScale backward)
 constexpr int kLnRows = 2;    // rows per iteration (LayerNorm backward: keeps registers low enough for 5-6 CTAs / SM)
 
@@ -151,9 +170,11 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
                                                           const float* __restrict__ w, const float* __restrict__ dres,
                                                           float* __restrict__ dx,
                                                           const BrT* __restrict__ branch, const float* __restrict__ gamma,
-                                                          BrT* __restrict__ dbranch, float* __restrict__ ws,
+                                                          BrT* __restrict__ dbranch, const DropDev dd, float* __restrict__ ws,
                                                           long long rows, int d) {
   __shared__ float red[2][8 * 2 * kLnRows];
+  const uint32_t dkey = (FUSE && dd.seed != nullptr) ? drop_mix(dd.salt, __ldg(dd.seed)) : 0u;
+  const float dscale = drop_scale(dd.thr);
   const int c = threadIdx.x * 4;
   const bool active = c < d;
   const int nwarps = blockDim.x >> 5;
@@ -205,10 +226,14 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
         store4(dx + row * d + c, o);
         if (FUSE) {
           const float4 br = load4(branch + row * d + c);
-          float4 dbr = make_float4(o.x * gm.x, o.y * gm.y, o.z * gm.z, o.w * gm.w);
+          // x1 = x + gamma * row_scale * drop(branch): `br` is the stored dropped branch, bm = mask * scale * row_scale
+          const float4 bm = branch_mul4(dd, dkey, dscale, row, d, c);
+          float4 dbr = make_float4(o.x * gm.x * bm.x, o.y * gm.y * bm.y, o.z * gm.z * bm.z, o.w * gm.w * bm.w);
           store4(dbranch + row * d + c, dbr);
           if (sizeof(BrT) == 2) dbr = bf16_round4(dbr);  // the bias gradient sums what the bf16 consumer sees
-          ag.x += o.x * br.x; ag.y += o.y * br.y; ag.z += o.z * br.z; ag.w += o.w * br.w;
+          float rs = 1.f;
+          if (dd.row_scale != nullptr) rs = __ldg(dd.row_scale + dd.row0 + row);
+          ag.x += o.x * br.x * rs; ag.y += o.y * br.y * rs; ag.z += o.z * br.z * rs; ag.w += o.w * br.w * rs;
           abb.x += dbr.x; abb.y += dbr.y; abb.z += dbr.z; abb.w += dbr.w;
         }
       }
@@ -229,9 +254,12 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
 template <typename BrT>
 __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __restrict__ dx, const BrT* __restrict__ branch,
                                                              const float* __restrict__ gamma, BrT* __restrict__ dbranch,
-                                                             bool need_dgamma, float* __restrict__ ws, long long rows, int d) {
+                                                             bool need_dgamma, const DropDev dd, float* __restrict__ ws, long long rows,
+                                                             int d) {
   const int c = threadIdx.x * 4;
   if (c >= d) return;
+  const uint32_t dkey = dd.seed != nullptr ? drop_mix(dd.salt, __ldg(dd.seed)) : 0u;
+  const float dscale = drop_scale(dd.thr);
   float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
   if (gamma != nullptr) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
@@ -248,10 +276,13 @@ __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __rest
 #pragma unroll
     for (int j = 0; j < kColRows; ++j) {
       if (r0 + j < rows) {
-        float4 o = make_float4(g[j].x * gm.x, g[j].y * gm.y, g[j].z * gm.z, g[j].w * gm.w);
+        const float4 bm = branch_mul4(dd, dkey, dscale, r0 + j, d, c);
+        float4 o = make_float4(g[j].x * gm.x * bm.x, g[j].y * gm.y * bm.y, g[j].z * gm.z * bm.z, g[j].w * gm.w * bm.w);
         store4(dbranch + (r0 + j) * d + c, o);
         if (sizeof(BrT) == 2) o = bf16_round4(o);
-        ag.x += g[j].x * br[j].x; ag.y += g[j].y * br[j].y; ag.z += g[j].z * br[j].z; ag.w += g[j].w * br[j].w;
+        float rs = 1.f;
+        if (dd.row_scale != nullptr) rs = __ldg(dd.row_scale + dd.row0 + r0 + j);
+        ag.x += g[j].x * br[j].x * rs; ag.y += g[j].y * br[j].y * rs; ag.z += g[j].z * br[j].z * rs; ag.w += g[j].w * br[j].w * rs;
         ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
       }
     }
@@ -325,6 +356,28 @@ extern "C" int mome_ln_fwd(const float* x, const float* weight, const float* bia
   return check_launch("ln_fwd");
 }
 
+static DropDev drop_dev(const MomeDropout* drop) {
+  DropDev dd{nullptr, nullptr, 0, 0u, 0u};
+  if (drop != nullptr) {
+    dd.seed = (drop->seed != nullptr && drop->p > 0.f) ? drop->seed : nullptr;
+    dd.row_scale = drop->row_scale;
+    dd.row0 = drop->row0;
+    dd.salt = drop->salt;
+    dd.thr = drop_threshold(drop->p);
+  }
+  return dd;
+}
+
+// stochastic-depth multipliers: one draw per (sample, salt), 24-bit resolution
+__global__ void droppath_scales_kernel(const int32_t* __restrict__ row_sample, long long rows, const uint32_t* __restrict__ seed,
+                                       uint32_t salt, float p, float* __restrict__ out) {
+  const uint32_t key = drop_mix(salt, __ldg(seed));
+  const uint32_t thr = static_cast<uint32_t>(p * 16777216.f);
+  const float keep = 1.f / (1.f - p);
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[r] = (drop_mix(static_cast<uint32_t>(row_sample[r]), key) >> 8) >= thr ? keep : 0.f;
+}
+
 static int col_threads(int64_t d) { return static_cast<int>(((d / 4) + 31) / 32 * 32); }
 static int col_grid(int64_t rows, int ctas_per_sm, int rows_per_iter = kColRows) {
   const long long groups = (rows + rows_per_iter - 1) / rows_per_iter;
@@ -347,16 +400,17 @@ extern "C" size_t mome_reduce_ws_bytes(int64_t cols) {
 template <bool FUSE>
 static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd, const float* weight,
                          const float* dres, float* dx_out, float* dweight, float* dbias, const void* branch, const float* gamma,
-                         void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, float* ws, cudaStream_t s) {
+                         void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, const DropDev& dd, float* ws,
+                         cudaStream_t s) {
   const int threads = col_threads(d), grid = col_grid(rows, 5, kLnRows);
   if (dy_dtype == MOME_BF16)
     ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE><<<grid, threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
-        static_cast<__nv_bfloat16*>(dbranch), ws, rows, (int)d);
+        static_cast<__nv_bfloat16*>(dbranch), dd, ws, rows, (int)d);
   else
     ln_bwd_cols_kernel<float, float, FUSE><<<grid, threads, 0, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out,
                                                                      static_cast<const float*>(branch), gamma,
-                                                                     static_cast<float*>(dbranch), ws, rows, (int)d);
+                                                                     static_cast<float*>(dbranch), dd, ws, rows, (int)d);
   int rc = check_launch(FUSE ? "ln_bwd_scale" : "ln_bwd");
   if (rc != MOME_OK) return rc;
   ColOuts o{{dweight, dbias, dgamma, dbias_br}, (int)d};
@@ -370,24 +424,24 @@ extern "C" int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const f
   MOME_REQUIRE_WS("ln_bwd", mome_reduce_ws_bytes(d));
   if (rows == 0) return MOME_OK;
   return ln_bwd_launch<false>(dy, dy_dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, nullptr, nullptr, nullptr, nullptr,
-                              nullptr, rows, d, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
+                              nullptr, rows, d, drop_dev(nullptr), static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
                                  const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                                  const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
-                                 int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream) {
+                                 int64_t rows, int64_t d, const MomeDropout* drop, void* ws, size_t ws_bytes, void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "ln_bwd_scale: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
   MOME_REQUIRE(branch != nullptr && dbranch != nullptr, "ln_bwd_scale: branch / dbranch must be given");
   MOME_REQUIRE_WS("ln_bwd_scale", mome_reduce_ws_bytes(d));
   if (rows == 0) return MOME_OK;
   return ln_bwd_launch<true>(dy, dtype, x, mean, rstd, weight, dres, dx_out, dweight, dbias, branch, gamma, dbranch, dgamma,
-                             dbias_branch, rows, d, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
+                             dbias_branch, rows, d, drop_dev(drop), static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
-                              int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* ws, size_t ws_bytes,
-                              void* stream) {
+                              int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, const MomeDropout* drop,
+                              void* ws, size_t ws_bytes, void* stream) {
   MOME_REQUIRE(d % 4 == 0 && d <= 1024, "scale_bwd: d=%lld unsupported (multiple of 4, <= 1024)", (long long)d);
   MOME_REQUIRE(branch_dtype == dbranch_dtype, "scale_bwd: branch and dbranch dtypes must match");
   MOME_REQUIRE_WS("scale_bwd", mome_reduce_ws_bytes(d));
@@ -395,12 +449,13 @@ extern "C" int mome_scale_bwd(const float* dx, const void* branch, int branch_dt
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int threads = col_threads(d), grid = col_grid(rows, 6);
   float* w = static_cast<float*>(ws);
+  const DropDev dd = drop_dev(drop);
   if (branch_dtype == MOME_BF16)
     scale_bwd_cols_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(dx, static_cast<const __nv_bfloat16*>(branch), gamma,
-                                                                   static_cast<__nv_bfloat16*>(dbranch), dgamma != nullptr, w, rows, (int)d);
+                                                                   static_cast<__nv_bfloat16*>(dbranch), dgamma != nullptr, dd, w, rows, (int)d);
   else
     scale_bwd_cols_kernel<float><<<grid, threads, 0, s>>>(dx, static_cast<const float*>(branch), gamma, static_cast<float*>(dbranch),
-                                                          dgamma != nullptr, w, rows, (int)d);
+                                                          dgamma != nullptr, dd, w, rows, (int)d);
   int rc = check_launch("scale_bwd");
   if (rc != MOME_OK) return rc;
   ColOuts o{{dgamma, dbias, nullptr, nullptr}, (int)d};
@@ -425,6 +480,15 @@ extern "C" int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols,
   if (rc != MOME_OK) return rc;
   ColOuts o{{out, nullptr, nullptr, nullptr}, (int)cols};
   return colreduce_launch(w, (int)slabs, (int)cols, o, s);
+}
+
+extern "C" int mome_droppath_scales(const int32_t* row_sample, int64_t rows, const uint32_t* seed, uint32_t salt, float p, float* out,
+                                    void* stream) {
+  MOME_REQUIRE(p >= 0.f && p < 1.f && seed != nullptr, "droppath_scales: need 0 <= p < 1 and a seed");
+  if (rows == 0) return MOME_OK;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, sm_count() * 4LL)));
+  droppath_scales_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_sample, rows, seed, salt, p, out);
+  return check_launch("droppath_scales");
 }
 
 // out[j] += sum_p partials[p][j] (second stage for partial column sums written by a GEMM epilogue)

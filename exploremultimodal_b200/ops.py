@@ -33,6 +33,21 @@ class PackedLayout:
         self.num_seqs = num_seqs
         self.max_seq_len = max_seq_len
 
+    def row_sample(self):
+        """int32 [tokens]: index of the sequence (sample) each packed row belongs to (stochastic depth draws
+        one Bernoulli per sample and block, reference timm DropPath)."""
+        if getattr(self, '_row_sample', None) is None:
+            desc = self.seq_desc.cpu()
+            rs = torch.zeros(self.tokens, dtype=torch.int32)
+            for i in range(desc.shape[0]):
+                s0, l0, s1, l1 = (int(v) for v in desc[i])
+                # one draw per sequence: before the fusion layer a sample's text and image halves are separate
+                # sequences (separate Block calls, hence independent DropPath draws, in the reference too)
+                rs[s0:s0 + l0] = i
+                rs[s1:s1 + l1] = i
+            self._row_sample = rs.to(self.seq_desc.device)
+        return self._row_sample
+
     def routing(self):
         """(route, first_row, rows) per group — what the bit-exact routing test compares."""
         return [(r, s, n) for (s, n, r) in self.groups]
@@ -124,23 +139,26 @@ def gemm(code, a_major, b_major, epilogue, out_code, N, lda, ldb, ldo, groups, l
     L.check(L.lib().mome_gemm(C.byref(args), L.stream()), 'mome_gemm')
 
 
-def attn_fwd(qkv, lay, key_mask, num_heads, scale):
+def attn_fwd(qkv, lay, key_mask, num_heads, scale, drop=None):
+    """drop: None or (seed int32 device tensor, salt, p) — dropout on the probabilities."""
     tokens, d3 = qkv.shape
     d = d3 // 3
     out = torch.empty(tokens, d, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(lay.num_seqs * num_heads * lay.max_seq_len, dtype=torch.float32, device=qkv.device)
     L.check(L.lib().mome_attn_fwd(qkv.data_ptr(), L.dtype_code(qkv), lay.seq_desc.data_ptr(), L.ptr(key_mask),
                                   out.data_ptr(), lse.data_ptr(), tokens, lay.num_seqs, lay.max_seq_len, num_heads,
-                                  scale, L.stream()), 'mome_attn_fwd')
+                                  scale, drop[0].data_ptr() if drop else None, drop[1] if drop else 0,
+                                  drop[2] if drop else 0.0, L.stream()), 'mome_attn_fwd')
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lay, key_mask, lse, num_heads, scale):
+def attn_bwd(qkv, out, dout, lay, key_mask, lse, num_heads, scale, drop=None):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     L.check(L.lib().mome_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), L.dtype_code(qkv),
                                   lay.seq_desc.data_ptr(), L.ptr(key_mask), lse.data_ptr(), dqkv.data_ptr(),
                                   delta.data_ptr(), qkv.shape[0], lay.num_seqs, lay.max_seq_len, num_heads, scale,
+                                  drop[0].data_ptr() if drop else None, drop[1] if drop else 0, drop[2] if drop else 0.0,
                                   L.stream()), 'mome_attn_bwd')
     return dqkv
 
@@ -154,7 +172,7 @@ def scale_bwd(dx, branch, gamma, dbranch, dgamma, dbias, first_row=0, rows=None)
     ws = reduce_ws(dx.device)
     L.check(L.lib().mome_scale_bwd(dx.data_ptr() + first_row * d * 4, branch.data_ptr() + first_row * d * es, code,
                                    L.ptr(gamma), dbranch.data_ptr() + first_row * d * es, code, L.ptr(dgamma),
-                                   L.ptr(dbias), rows, d, ws.data_ptr(), ws.numel(), L.stream()), 'mome_scale_bwd')
+                                   L.ptr(dbias), rows, d, None, ws.data_ptr(), ws.numel(), L.stream()), 'mome_scale_bwd')
 
 
 def colsum(x, out, first_row=0, rows=None):
@@ -181,7 +199,7 @@ class BlockParams:
     """Tensors one block call needs, gathered by `Block` (vlmo.py). Weights `w_*` are in the compute
     dtype (bf16 copies refreshed after each optimizer step, or the fp32 parameters themselves)."""
     __slots__ = ('code', 'eps', 'num_heads', 'gamma_1', 'gamma_2', 'n1w', 'n1b', 'n2w', 'n2b', 'qkv_bias',
-                 'w_qkv', 'w_proj', 'proj_b', 'experts')
+                 'w_qkv', 'w_proj', 'proj_b', 'experts', 'drop')
 
 
 def _fill_common(a, lay, key_mask, p, x, hid):
@@ -202,8 +220,20 @@ def _fill_common(a, lay, key_mask, p, x, hid):
         g.w1, g.b1, g.w2, g.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
 
 
+def _fill_dropout(a, lay, p, row_scales):
+    """p.drop: None or dict(seed=int32 device tensor, salt=int, p_attn, p_hidden, p_branch, p_path)."""
+    dr = p.drop
+    if not dr:
+        return
+    a.drop_seed, a.drop_salt = dr['seed'].data_ptr(), dr['salt'] & 0xffffffff
+    a.p_attn, a.p_hidden, a.p_branch, a.p_path = dr['p_attn'], dr['p_hidden'], dr['p_branch'], dr['p_path']
+    if dr['p_path'] > 0:
+        a.row_sample = lay.row_sample().data_ptr()
+        a.row_scale1, a.row_scale2 = row_scales[0].data_ptr(), row_scales[1].data_ptr()
+
+
 def _fill_saved(a, saved):
-    (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2) = saved
+    (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2) = saved[:15]
     a.x, a.h, a.mean1, a.rstd1 = x.data_ptr(), h.data_ptr(), mean1.data_ptr(), rstd1.data_ptr()
     a.qkv, a.o, a.lse, a.br1, a.x1 = qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), br1.data_ptr(), x1.data_ptr()
     a.h2, a.mean2, a.rstd2 = h2.data_ptr(), mean2.data_ptr(), rstd2.data_ptr()
@@ -228,10 +258,13 @@ def block_forward(x, lay, key_mask, p):
     mean1, rstd1, mean2, rstd2 = stats[0], stats[1], stats[2], stats[3]
     lse = torch.empty(lay.num_seqs * p.num_heads * lay.max_seq_len, **f32)
     x1, x2 = torch.empty_like(x), torch.empty_like(x)
-    saved = (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2)
+    # stochastic-depth multipliers per row and branch (written by the forward, re-read by the backward)
+    row_scales = torch.empty(2, tokens if (p.drop and p.drop['p_path'] > 0) else 0, **f32)
+    saved = (x, h, mean1, rstd1, qkv, o, lse, br1, x1, h2, mean2, rstd2, gp, u, br2, row_scales)
     a = L.BlockArgs()
     _fill_common(a, lay, key_mask, p, x, hid)
     _fill_saved(a, saved)
+    _fill_dropout(a, lay, p, row_scales)
     a.x2 = x2.data_ptr()
     L.check(L.lib().mome_block_fwd(C.byref(a), L.stream()), 'mome_block_fwd')
     return x2, saved
@@ -264,6 +297,7 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     a = L.BlockArgs()
     _fill_common(a, lay, key_mask, p, x, hid)
     _fill_saved(a, saved)
+    _fill_dropout(a, lay, p, saved[15])
     keep = []  # scratch tensors must outlive the (asynchronous) call: the caching allocator is stream ordered
     for i, (s, n, route) in enumerate(lay.groups):
         dw1, db1 = buf(('mlp', route, 0), hid, d), buf(('mlp', route, 1), hid)
@@ -309,9 +343,10 @@ class MomeBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, holder, lay, key_mask, x, *params):
         p = holder.block_params(lay)
+        p.drop = holder.next_dropout() if hasattr(holder, 'next_dropout') else None
         with torch.no_grad():
             out, saved = block_forward(x.contiguous(), lay, key_mask, p)
-        ctx.holder, ctx.lay, ctx.key_mask = holder, lay, key_mask
+        ctx.holder, ctx.lay, ctx.key_mask, ctx.drop = holder, lay, key_mask, p.drop
         ctx.save_for_backward(*saved)
         ctx.has = [t is not None for t in params]
         return out
@@ -324,6 +359,7 @@ class MomeBlockFn(torch.autograd.Function):
         lay = ctx.lay
         holder = ctx.holder
         p = holder.block_params(lay)
+        p.drop = ctx.drop  # same seed tensor, salt and rates as the forward: the masks are regenerated, not stored
         slots = list(MomeBlockFn.SLOTS)
         for (_, _, route) in lay.groups:
             slots += [('mlp', route, i) for i in range(4)]

@@ -187,6 +187,8 @@ class Block(nn.Module):
             self.gamma_1, self.gamma_2 = None, None
         self.precision = precision
         self._cache = _VersionedCache()
+        self.layer_index = 0      # set by VLMO
+        self.drop_state = None    # {'seed': int32 device tensor, 'calls': int}; shared by all blocks of a VLMO
 
     # ---- kernel-side view of the parameters
     def _weight(self, name, param, code):
@@ -216,6 +218,7 @@ class Block(nn.Module):
         p.w_qkv = self._weight('qkv', a.qkv.weight, code)
         p.w_proj = self._weight('proj', a.proj.weight, code)
         p.proj_b = a.proj.bias.detach()
+        p.drop = None
         p.experts = {}
         for (_, _, route) in lay.groups:
             m = self.mlp[route]
@@ -232,12 +235,23 @@ class Block(nn.Module):
             ps += [m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
         return ps
 
+    # ---- dropout (training mode, bf16 path): masks are a pure function of (device seed, salt, element), see
+    # csrc/dropout.cuh. The seed tensor is bumped once per step by the owner (VLMO.advance_dropout / VlmoModule.forward);
+    # the salt names the call: layer index and the running count of block calls since the seed was bumped.
+    def next_dropout(self):
+        if not self.training or not (self.drop_rate > 0 or self.attn_drop_rate > 0 or self.drop_path_rate > 0):
+            return None
+        if self.precision != 'bf16':
+            raise NotImplementedError('dropout / stochastic depth are implemented on the bf16 path only')
+        st = self.drop_state
+        if st is None or st['seed'].device != self.norm1.weight.device:
+            st = self.drop_state = {'seed': torch.zeros(1, dtype=torch.int32, device=self.norm1.weight.device), 'calls': 0}
+        st['calls'] += 1
+        return dict(seed=st['seed'], salt=(self.layer_index * 8 + st['calls'] * 4096) & 0x7fffffff, p_attn=self.attn_drop_rate,
+                    p_hidden=self.drop_rate, p_branch=self.drop_rate, p_path=self.drop_path_rate)
+
     def forward_packed(self, x, lay, key_mask):
         """x: fp32 [tokens, d] packed residual stream; returns the same."""
-        if self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError(
-                'libmome kernels do not implement dropout / stochastic depth yet; build the model with '
-                'drop_rate = attn_drop_rate = drop_path_rate = 0 (see DESIGN.md, scope)')
         return ops.MomeBlockFn.apply(self, lay, key_mask, x, *self._param_list(lay))
 
     def forward(self, x, mask=None, route='vl'):
@@ -290,6 +304,9 @@ class VLMO(nn.Module):
         self.apply(self._init_weights)
         self._layouts = {}
         self._pe_cache = _VersionedCache()
+        self._drop_state = None
+        for i, b in enumerate(self.blocks):
+            b.layer_index = i
         self.route_log = None  # set to a list to record (layer, route, first_row, rows) per expert group
 
     def _init_weights(self, m):
@@ -315,6 +332,17 @@ class VLMO(nn.Module):
         self.precision = precision
         for b in self.blocks:
             b.precision = precision
+
+    def advance_dropout(self):
+        """Start a new step's dropout masks: bump the device seed (a captured CUDA graph replays this increment,
+        so masks differ from step to step under a graph too) and restart the per-step call counter."""
+        dev = self.pos_embed.device
+        if self._drop_state is None or self._drop_state['seed'].device != dev:
+            self._drop_state = {'seed': torch.zeros(1, dtype=torch.int32, device=dev), 'calls': 0}
+            for b in self.blocks:
+                b.drop_state = self._drop_state
+        self._drop_state['seed'].add_(1)
+        self._drop_state['calls'] = 0
 
     def _autocast(self):
         return torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.precision == 'bf16')

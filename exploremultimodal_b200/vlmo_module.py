@@ -170,6 +170,8 @@ class VlmoModule(nn.Module):
     # ---- reference vlmo_module.py:395-436
     def forward(self, batch):
         batch = defaultdict(lambda: None, batch)
+        if self.training:
+            self.transformer.advance_dropout()
         ret = dict()
         if len(self.loss_names) == 0:
             ret.update(self.infer(batch))

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MOME_ABI_VERSION 4
+#define MOME_ABI_VERSION 5
 #define MOME_MAX_GROUPS 4
 
 enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
@@ -30,6 +30,17 @@ int mome_version(void);
 const char* mome_last_error(void);
 /* number of SMs of the current device (grid sizing; 148 on B200) */
 int mome_sm_count(void);
+
+/* Dropout of a branch in the backward kernels: `branch` is the stored, already dropped forward value; the
+ * mask of element (row0 + r, c) is regenerated (csrc/dropout.cuh). row_scale: stochastic-depth multipliers
+ * indexed by global row, or NULL. Pass drop = NULL for no dropout and no row scaling. */
+typedef struct {
+  const uint32_t* seed; /* device scalar, NULL = no element dropout */
+  const float* row_scale;
+  int64_t row0;
+  uint32_t salt;
+  float p;
+} MomeDropout;
 
 /* ---- K3: LayerNorm and the HBM-bound epilogues -------------------------------------------------
  * reference: vlmo.py:26-36 (LayerNorm factory), vlmo.py:188,192,196 (norm1/norm2), vlmo.py:355,376,
@@ -48,13 +59,17 @@ int mome_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
 int mome_ln_bwd_scale(const void* dy, int dtype, const float* x, const float* mean, const float* rstd,
                       const float* weight, const float* dres, float* dx_out, float* dweight, float* dbias,
                       const void* branch, const float* gamma, void* dbranch, float* dgamma, float* dbias_branch,
-                      int64_t rows, int64_t d, void* ws, size_t ws_bytes, void* stream);
+                      int64_t rows, int64_t d, const MomeDropout* drop, void* ws, size_t ws_bytes, void* stream);
 /* LayerScale backward (reference vlmo.py:194-196, `x + gamma * branch`):
  *   dbranch = gamma * dx (cast to dbranch_dtype); dgamma += sum_rows dx * branch;
  *   dbias += sum_rows dbranch (bias of the Linear that produced `branch`). gamma may be NULL (=1). */
 int mome_scale_bwd(const float* dx, const void* branch, int branch_dtype, const float* gamma, void* dbranch,
-                   int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, void* ws, size_t ws_bytes,
-                   void* stream);
+                   int dbranch_dtype, float* dgamma, float* dbias, int64_t rows, int64_t d, const MomeDropout* drop,
+                   void* ws, size_t ws_bytes, void* stream);
+/* out[row] = stochastic-depth multiplier of row's sample: 0 with probability p, else 1 / (1 - p); one draw per
+ * (sample, salt). row_sample[row] = index of the sequence / sample the row belongs to. reference: timm DropPath. */
+int mome_droppath_scales(const int32_t* row_sample, int64_t rows, const uint32_t* seed, uint32_t salt, float p,
+                         float* out, void* stream);
 /* out[j] += sum_rows x[r, j]  (bias gradients of qkv / fc1) */
 int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, float* out, void* ws, size_t ws_bytes,
                 void* stream);
@@ -99,6 +114,8 @@ typedef struct {
   const float* bias; /* [N] or NULL */
   const float* res;  /* fp32 [M, ldres] (RESIDUAL) */
   const void* aux;   /* operand dtype [M, ldaux] (DGELU) */
+  int64_t row0;      /* row of the packed token buffer this group starts at (dropout masks and row_scale are
+                        indexed by that global row, so forward and backward agree however rows are grouped) */
   float* colsum;     /* optional (STORE / DGELU), ZEROED fp32 [ceil(M/32), N]: row i receives the column sums of
                         the stored out rows [32 i, 32 i + 32); mome_colreduce adds the rows (bias gradient) */
 } MomeGemmGroup;
@@ -115,6 +132,14 @@ typedef struct {
   int64_t lda, ldb, ldo, ldo2, ldres, ldaux; /* in elements */
   const float* gamma; /* [N] or NULL (RESIDUAL) */
   MomeGemmGroup group[MOME_MAX_GROUPS];
+  /* Dropout (bf16 path; reference vlmo.py:97 proj_drop, timm Mlp drop, DropPath at vlmo.py:194-196). NULL seed = off.
+   *   GELU    : out = drop(gelu(z)), out2 = gelu'(z) * mask            (timm Mlp's dropout after the activation)
+   *   RESIDUAL: out2 = b = drop(acc + bias); out = res + gamma * row_scale[row] * b
+   * Masks are a pure function of (*drop_seed, drop_salt, global row, column): see csrc/dropout.cuh. */
+  const uint32_t* drop_seed; /* device scalar */
+  const float* row_scale;    /* RESIDUAL: per-row multiplier of the branch (stochastic depth), [tokens] or NULL */
+  uint32_t drop_salt;
+  float drop_p;
 } MomeGemmArgs;
 
 int mome_gemm(const MomeGemmArgs* args, void* stream);
@@ -124,14 +149,17 @@ int mome_gemm(const MomeGemmArgs* args, void* stream);
  * merge heads). qkv is the [tokens, 3*d] output of the qkv GEMM (column = s*d + h*64 + e).
  * A sequence is up to two row ranges of the packed buffer ([text | image] after the fusion layer,
  * one range before it): seq_desc[4*s + {0,1,2,3}] = {start0, len0, start1, len1}.
- * key_mask[row] = 1 keeps the key, 0 excludes it; query rows are never masked. head_dim is 64. */
+ * key_mask[row] = 1 keeps the key, 0 excludes it; query rows are never masked. head_dim is 64.
+ * drop_seed (device scalar, NULL = off) / drop_salt / drop_p: dropout on the attention probabilities (vlmo.py:93),
+ * bf16 path only; the backward must be given the same three values (masks are regenerated, csrc/dropout.cuh). */
 int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out,
                   float* lse, int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads,
-                  float scale, void* stream);
+                  float scale, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream);
 /* dqkv gets every element of its [tokens, 3*d] rows written. */
 int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
                   const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens,
-                  int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, void* stream);
+                  int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, const uint32_t* drop_seed,
+                  uint32_t drop_salt, float drop_p, void* stream);
 
 /* ---- K4: ITC head — similarity GEMM fused with softmax cross-entropy -------------------------------
  * reference: objectives.py:99-108 (global-reduce logits), 166-171 (naive), 173-180 (CE + accuracy),
@@ -217,6 +245,15 @@ typedef struct {
   float* s_dx1;              /* scratch fp32 [tokens, d] */
   float* s_delta;            /* scratch fp32, same size as lse */
   void* ws; size_t ws_bytes; /* mome_reduce_ws_bytes(max(hid, 3d)) */
+  /* Dropout, bf16 path only (reference Block: attn_drop vlmo.py:93, proj_drop :97, timm Mlp drop, DropPath
+   * :194-196). drop_seed NULL or all p == 0: off. Call sites use drop_salt + {0: attention probabilities,
+   * 1: proj output, 2: after GELU, 3: fc2 output, 4 / 5: stochastic depth of the attention / FFN branch}. */
+  const uint32_t* drop_seed;   /* device scalar, bumped by the caller once per step */
+  const int32_t* row_sample;   /* [tokens] index of the sample a row belongs to (needed when p_path > 0) */
+  float* row_scale1;           /* [tokens] stochastic-depth multipliers: written by the forward, read by the backward */
+  float* row_scale2;
+  uint32_t drop_salt;
+  float p_attn, p_hidden, p_branch, p_path;
 } MomeBlockArgs;
 
 int mome_block_fwd(const MomeBlockArgs* args, void* stream);

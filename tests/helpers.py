@@ -59,3 +59,54 @@ def oracle_state(cfg, requires_grad=True):
         for v in sd.values():
             v.requires_grad_(True)
     return sd
+
+
+# ---- numpy restatement of csrc/dropout.cuh (mask = pure function of seed, salt, element index) --------------
+import numpy as np  # noqa: E402
+
+
+def drop_mix(idx, key):
+    """murmur3 finaliser over (idx * golden + key), uint32 arithmetic (csrc/dropout.cuh::drop_mix)."""
+    h = (np.asarray(idx, dtype=np.uint64) * np.uint64(0x9E3779B1) + np.uint64(key)) & np.uint64(0xffffffff)
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85ebca6b)) & np.uint64(0xffffffff)
+    h ^= h >> np.uint64(13)
+    h = (h * np.uint64(0xc2b2ae35)) & np.uint64(0xffffffff)
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def drop_threshold(p):
+    return min(255, max(0, int(p * 256.0 + 0.5)))
+
+
+def matrix_drop_multipliers(seed, salt, p, rows, cols, row0=0):
+    """[rows, cols] multipliers (0 or 256 / (256 - thr)) of a row-major matrix whose first row is global row `row0`."""
+    thr = drop_threshold(p)
+    key = int(drop_mix(salt & 0xffffffff, seed))
+    e = (np.arange(row0, row0 + rows, dtype=np.uint64)[:, None] * np.uint64(cols) + np.arange(cols, dtype=np.uint64)[None, :])
+    word = drop_mix((e >> np.uint64(2)) & np.uint64(0xffffffff), key)
+    byte = (word >> (np.uint64(8) * (e & np.uint64(3)))) & np.uint64(255)
+    return torch.from_numpy(np.where(byte >= thr, 256.0 / (256 - thr), 0.0).astype(np.float32))
+
+
+def attn_drop_multipliers(seed, salt, p, S, H, max_seq_len):
+    """[S, H, N, N] multipliers of the attention probabilities (query major), N = max_seq_len."""
+    thr = drop_threshold(p)
+    key = int(drop_mix(salt & 0xffffffff, seed))
+    N = max_seq_len
+    kp2 = (N + 1) // 2
+    sh = (np.arange(S, dtype=np.uint64)[:, None] * np.uint64(H) + np.arange(H, dtype=np.uint64)[None, :])          # [S, H]
+    row = ((sh[:, :, None] * np.uint64(N) + np.arange(N, dtype=np.uint64)[None, None, :]) * np.uint64(kp2))          # [S, H, N]
+    j = np.arange(N, dtype=np.uint64)
+    idx = (row[..., None] + (j >> np.uint64(1))[None, None, None, :]) & np.uint64(0xffffffff)
+    word = drop_mix(idx, key)
+    byte = (word >> (np.uint64(16) * (j & np.uint64(1)))[None, None, None, :]) & np.uint64(255)
+    return torch.from_numpy(np.where(byte >= thr, 256.0 / (256 - thr), 0.0).astype(np.float32))
+
+
+def droppath_multipliers(seed, salt, p, samples):
+    key = int(drop_mix(salt & 0xffffffff, seed))
+    h = drop_mix(np.arange(samples, dtype=np.uint64), key)
+    thr = int(np.float32(p) * np.float32(16777216.0))
+    return torch.from_numpy(np.where((h >> np.uint64(8)) >= thr, 1.0 / (1.0 - p), 0.0).astype(np.float32))

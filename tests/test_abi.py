@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     _ensure_built()
     handle = ctypes.CDLL(_lib.LIB_PATH)
     declared = _declared_functions()
-    assert len(declared) >= 25
+    assert len(declared) >= 26
     for name in declared:
         assert hasattr(handle, name), f'{name} declared in include/mome.h but not exported'
     assert sorted(_lib.exported_symbols()) == declared, 'ctypes binding and header disagree'
@@ -37,12 +37,13 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # MomeGemmGroup: 10 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
-    assert ctypes.sizeof(_lib.GemmGroup) == 80
-    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 80
+    # MomeGemmGroup: 11 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
+    assert ctypes.sizeof(_lib.GemmGroup) == 88
+    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 88 + 24
     # MomeBlockGroup: 11 x 8; MomeBlockArgs: 6 x int32 + 3 x int64 + 2 x float + 12 pointers + 4 groups + 38 pointers + size_t
     assert ctypes.sizeof(_lib.BlockGroup) == 88
-    assert ctypes.sizeof(_lib.BlockArgs) == 24 + 24 + 8 + 12 * 8 + 4 * 88 + 38 * 8 + 8
+    assert ctypes.sizeof(_lib.BlockArgs) == 24 + 24 + 8 + 12 * 8 + 4 * 88 + 38 * 8 + 8 + 4 * 8 + 24
+    assert ctypes.sizeof(_lib.Dropout) == 32
 
 
 def test_state_dict_layout_matches_reference():
