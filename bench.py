@@ -38,6 +38,9 @@ def parse():
     ap.add_argument('--lengths', default='full', choices=['full', 'realistic'])
     ap.add_argument('--cpu-batch', type=int, default=2, help='batch of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dropout', default='shipped', choices=['shipped', 'off'],
+                    help="'shipped': drop_rate / attn_drop_rate / drop_path_rate = 0.1 as in the reference's conf/model/vlmo_base.yaml; "
+                         "'off': the parity configuration")
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--ncu-step', action='store_true',
                     help='after warm-up run ONE eager step between cudaProfilerStart/Stop and exit '
@@ -186,7 +189,7 @@ def run_mome(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    cfg = make_config(args.model, loss_names=('mlm', 'itc', 'itm'), global_reduce=world > 1, parity=True)
+    cfg = make_config(args.model, loss_names=('mlm', 'itc', 'itm'), global_reduce=world > 1, parity=args.dropout == 'off')
     cfg.model.precision = args.precision
     torch.manual_seed(0)
     model = build_model(cfg).to(dev).train()
@@ -350,7 +353,8 @@ def run_mome(args):
         'config': {'workload': f'{args.model} pretrain step MLM+ITC+ITM fwd+bwd+AdamW (BASELINE configs[1]: global batch '
                                f'{world * B} = {B}/GPU x {world})', 'per_gpu_batch': B, 'global_batch': world * B,
                    'img': 224, 'text_len': 40, 'lengths': args.lengths, 'parallelism': f'dp{world}',
-                   'dropout': 0.0, 'cuda_graph': bool(graph is not None),
+                   'dropout': {'drop_rate': cfg.model.drop_rate, 'attn_drop_rate': cfg.model.attn_drop_rate,
+                               'drop_path_rate': cfg.model.drop_path_rate}, 'cuda_graph': bool(graph is not None),
                    'l2': 'per-step working set (~50 GB of activations) far exceeds the 126 MB L2; no flush needed'},
         'samples_per_sec_per_gpu': value / world,
         'model_tflops_per_gpu': fps * B / (ms_step * 1e-3) / 1e12,

@@ -108,7 +108,7 @@ def test_ln_bwd_scale_fused(bf16, rows, d):
     dbr1 = torch.empty(rows, d, dtype=dt, device=_dev())
     L.check(L.lib().mome_ln_bwd_scale(dy.data_ptr(), code, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(),
                                       dres.data_ptr(), dx1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), branch.data_ptr(),
-                                      gamma.data_ptr(), dbr1.data_ptr(), dg1.data_ptr(), dbb1.data_ptr(), rows, d,
+                                      gamma.data_ptr(), dbr1.data_ptr(), dg1.data_ptr(), dbb1.data_ptr(), rows, d, None,
                                       ops.reduce_ws(_dev()).data_ptr(), ops.reduce_ws(_dev()).numel(), L.stream()), 'ln_bwd_scale')
     assert torch.equal(dx0, dx1) and torch.equal(dbr0, dbr1)
     for a, c in ((dw0, dw1), (db0, db1), (dg0, dg1), (dbb0, dbb1)):
