@@ -286,9 +286,11 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma_kernel(const __nv_bfloa
     l1 = l1 * c1 + quad_sum(rs1);
     m0 = mn0;
     m1 = mn1;
+    if (__any_sync(0xffffffffu, c0 != 1.f || c1 != 1.f)) {  // the running max rarely moves after the first tiles
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+      for (int nt = 0; nt < 8; ++nt) {
+        o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+      }
     }
     if (DROP) {  // the normaliser l keeps the undropped probabilities; only what multiplies V is dropped
 #pragma unroll
@@ -578,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_mma_kernel(const __n
           const int nt = 2 * j + h2, c = nt * 8 + 2 * t;
           const float Da = Dq[c], Db = Dq[c + 1];
           const uint32_t w0 = pf[j][2 * h2], w1 = pf[j][2 * h2 + 1];
-          const uint32_t a0 = w0 & 0x7fff7fffu, a1 = w1 & 0x7fff7fffu;
+          const uint32_t a0 = DROP ? (w0 & 0x7fff7fffu) : w0, a1 = DROP ? (w1 & 0x7fff7fffu) : w1;
           const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a0));
           const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a1));
           if (DROP) {  // dP^T of dropped probabilities is zero, kept ones carry the scale
