@@ -194,8 +194,6 @@ def run_mome(args):
     torch.manual_seed(0)
     model = build_model(cfg).to(dev).train()
     model.transformer.img_mask_token.requires_grad_(False)  # unused without MIM
-    for blk in model.transformer.blocks:
-        blk.fused_grad_accumulation = True  # gradients are all-reduced by this script, not by DDP hooks
     params = [p for p in model.parameters() if p.requires_grad]
     if world > 1:
         for p in model.parameters():
@@ -212,38 +210,15 @@ def run_mome(args):
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
 
-    flat_grads = None
-
-    def sync_grads():
-        """Data-parallel gradient all-reduce (mean) over NCCL, a few large buckets after backward."""
-        nonlocal flat_grads
-        if world == 1:
-            return
-        grads = [p.grad for p in params]
-        bucket, size = [], 0
-        for g in grads:
-            bucket.append(g)
-            size += g.numel()
-            if size >= 64 * 1024 * 1024:
-                _allreduce_bucket(bucket)
-                bucket, size = [], 0
-        if bucket:
-            _allreduce_bucket(bucket)
-
-    def _allreduce_bucket(bucket):
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+    from exploremultimodal_b200.ddp import GradSync
+    sync = GradSync(model, world)  # flat per-block gradient buffers, all-reduced on a side stream as blocks finish
 
     def step_body():
         opt.zero_grad(set_to_none=False)
         out = model(static_in)
         loss = sum(v for k, v in out.items() if 'task_loss' in k)
         loss.backward()
-        sync_grads()
+        sync.finish()
         opt.step()
         loss_dev.copy_(loss.detach().reshape(1))
 
@@ -252,8 +227,6 @@ def run_mome(args):
             static_in[k].copy_(v, non_blocking=True)
 
     # ---- warm-up (eager), then optionally capture the whole step in a CUDA graph
-    for p in params:
-        p.grad = torch.zeros_like(p)
     load_inputs()
     graph = None
     use_graph = not args.no_graph and not args.ncu_step

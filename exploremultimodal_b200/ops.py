@@ -347,6 +347,8 @@ class MomeBlockFn(torch.autograd.Function):
         with torch.no_grad():
             out, saved = block_forward(x.contiguous(), lay, key_mask, p)
         ctx.holder, ctx.lay, ctx.key_mask, ctx.drop = holder, lay, key_mask, p.drop
+        if any(ctx.needs_input_grad):
+            holder._pending_bwd = getattr(holder, '_pending_bwd', 0) + 1  # calls of this block awaiting their backward
         ctx.save_for_backward(*saved)
         ctx.has = [t is not None for t in params]
         return out
@@ -384,4 +386,9 @@ class MomeBlockFn(torch.autograd.Function):
             for i, t in enumerate(g[('mlp', route)]):
                 vals[('mlp', route, i)] = t
         out = [None if (slot in targets or not has) else vals[slot] for slot, has in zip(slots, ctx.has)]
+        # the last pending backward of this block in the step: its parameter gradients are final (ddp.GradSync)
+        holder._pending_bwd = getattr(holder, '_pending_bwd', 1) - 1
+        hook = getattr(holder, 'grads_ready_hook', None)
+        if hook is not None and holder._pending_bwd == 0:
+            hook(holder)
         return (None, None, None, dx, *out)
