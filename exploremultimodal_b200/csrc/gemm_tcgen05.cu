@@ -550,6 +550,11 @@ int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_
 
 }  // namespace
 
+// the same encoder for other translation units (attention_tc.cu); `map` is a CUtensorMap*
+int tma_encode_bf16_2d(void* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  return encode_bf16_2d(static_cast<CUtensorMap*>(map), base, inner, outer, ld, box_inner, box_outer);
+}
+
 int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
   MOME_REQUIRE(a->num_groups >= 1 && a->num_groups <= MOME_MAX_GROUPS, "gemm: num_groups %d", a->num_groups);
   MOME_REQUIRE(a->N > 0 && a->N % 32 == 0, "gemm(bf16): N=%lld must be a positive multiple of 32", (long long)a->N);

@@ -291,6 +291,13 @@ ATTN_CASES = [
     ([(0, 197, 0, 0)], 197, 3),
     ([(0, 40, 80, 197), (40, 40, 277, 197)], 80 + 394, 12),
     ([(0, 40, 40, 901)], 941, 2),
+    # tcgen05 forward (64 < max_seq_len <= 256): second range not on an 8-row boundary (gather path instead of TMA
+    # boxes), one-row second tile, exactly 256 keys, single short tile, ragged mix of text-like and image-like rows
+    ([(0, 13, 39, 100), (13, 13, 139, 100), (26, 13, 239, 100)], 339, 2),
+    ([(0, 129, 0, 0), (129, 100, 0, 0)], 229, 3),
+    ([(0, 40, 40, 216)], 256, 4),
+    ([(0, 65, 0, 0), (65, 9, 0, 0), (74, 128, 0, 0)], 202, 2),
+    ([(0, 24, 96, 197), (24, 24, 293, 60), (48, 24, 353, 197), (72, 24, 550, 1)], 551, 2),
 ]
 
 
@@ -321,6 +328,46 @@ def test_attention_fwd_bwd(bf16, case):
     assert torch.isfinite(dqkv.float()).all()
     for name, sl in (('dq', slice(0, d)), ('dk', slice(d, 2 * d)), ('dv', slice(2 * d, 3 * d))):
         assert rel_err(dqkv[:, sl], qd.grad[:, sl]) < (2e-2 if bf16 else FP32_TOL), name
+
+
+@pytest.mark.parametrize('drop', [False, True])
+@pytest.mark.parametrize('mask_kind', ['ones', 'random', 'pad'])
+def test_attention_tcgen05_forward_matches_mma_sync(drop, mask_kind, monkeypatch):
+    """The two bf16 forward kernels (tcgen05 / TMEM and mma.sync) implement one contract: same outputs, same
+    log-sum-exp, same dropout mask for a given (seed, salt). Fused [text | image] layout of the pre-training step."""
+    L, ops = _mods()
+    B, T, P, H = 6, 40, 197, 12
+    lay = ops.fused_layout(B, T, P, _dev())
+    qkv = _rand(lay.tokens, 3 * 64 * H, dtype=torch.bfloat16, seed=11)
+    g = torch.Generator().manual_seed(5)
+    if mask_kind == 'ones':
+        mask = torch.ones(lay.tokens, dtype=torch.uint8)
+    elif mask_kind == 'random':
+        mask = (torch.rand(lay.tokens, generator=g) > 0.2).to(torch.uint8)
+    else:
+        mask = torch.ones(lay.tokens, dtype=torch.uint8)
+        lens = torch.randint(5, T + 1, (B,), generator=g)
+        mask[:B * T] = (torch.arange(T)[None, :] < lens[:, None]).reshape(-1).to(torch.uint8)
+    mask[:B * T:T] = 1
+    mask = mask.to(_dev())
+    seed = torch.tensor([77], dtype=torch.int32, device=_dev())
+    dr = (seed, 3, 0.1) if drop else None
+    res = {}
+    for tc in ('0', '1'):
+        monkeypatch.setenv('MOME_ATTN_TC', tc)
+        n0 = L.lib().mome_launch_count()
+        res[tc] = ops.attn_fwd(qkv, lay, mask, H, 0.125, dr)
+        assert L.lib().mome_launch_count() == n0 + 1
+    (o0, l0), (o1, l1) = res['0'], res['1']
+    assert torch.isfinite(o1.float()).all()
+    assert (o0.float() - o1.float()).abs().max() <= 2.0 ** -6      # one bf16 ulp at |x| < 4
+    assert rel_err(o1, o0) < 4e-3
+    assert (l0 - l1).abs().max() < 1e-4
+    # and the mma.sync backward takes the tcgen05 forward's outputs
+    dout = _rand(lay.tokens, 64 * H, dtype=torch.bfloat16, seed=12)
+    g0 = ops.attn_bwd(qkv, o0, dout, lay, mask, l0, H, 0.125, dr)
+    g1 = ops.attn_bwd(qkv, o1, dout, lay, mask, l1, H, 0.125, dr)
+    assert rel_err(g1, g0) < 1e-2
 
 
 def test_attention_no_mask_pointer():

@@ -1,0 +1,88 @@
+"""Micro-benchmark / cross-check of the attention kernels at the shapes of the VLMo-base step (GPU only).
+
+    python tools/attn_bench.py [--batch 256] [--iters 20] [--no-bwd]
+
+For every layout of the step (fused [40 text | 197 image], split text / image, image only) runs the mma.sync
+kernels (MOME_ATTN_TC=0) and the tcgen05 kernels (MOME_ATTN_TC=1) on the same inputs, prints the largest
+difference between them (outputs, lse, gradients) and the CUDA-event time per launch of each."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from exploremultimodal_b200 import ops  # noqa: E402
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--heads', type=int, default=12)
+    ap.add_argument('--no-bwd', action='store_true')
+    ap.add_argument('--drop', type=float, default=0.1)
+    ap.add_argument('--tc', default='1', help='MOME_ATTN_TC value to compare against the mma.sync kernels')
+    ap.add_argument('--mask', default='ones', choices=['ones', 'random', 'pad'], help='key mask: all ones (the bench), 10 %% random zeros, or padded text (lengths 8..40)')
+    ap.add_argument('--only', default='', help='substring of the layout name to run')
+    a = ap.parse_args()
+    B, H, T, P = a.batch, a.heads, 40, 197
+    d = 64 * H
+    dev = torch.device('cuda')
+    layouts = [('fused 40+197', ops.fused_layout(B, T, P, dev)), ('split 40 / 197', ops.split_layout(B, T, P, dev)),
+               ('image 197', ops.single_layout(B, P, 'v', dev)), ('text 40', ops.single_layout(B, T, 'l', dev))]
+    seed = torch.tensor([1234], dtype=torch.int32, device=dev)
+    for name, lay in layouts:
+        if a.only not in name:
+            continue
+        g = torch.Generator(device='cuda').manual_seed(1)
+        qkv = torch.randn(lay.tokens, 3 * d, generator=g, device=dev).to(torch.bfloat16)
+        dout = torch.randn(lay.tokens, d, generator=g, device=dev).to(torch.bfloat16)
+        if a.mask == 'random':
+            mask = (torch.rand(lay.tokens, generator=g, device=dev) > 0.1).to(torch.uint8)
+        else:
+            mask = torch.ones(lay.tokens, dtype=torch.uint8, device=dev)
+            if a.mask == 'pad' and name != 'image 197':  # text rows come first in every layout that has text
+                lens = torch.randint(8, T + 1, (B,), generator=g, device=dev)
+                mask[:B * T] = (torch.arange(T, device=dev)[None, :] < lens[:, None]).reshape(-1).to(torch.uint8)
+        for drop in (None, (seed, 7, a.drop)):
+            res = {}
+            for tc in ('0', a.tc):
+                os.environ['MOME_ATTN_TC'] = tc
+                out, lse = ops.attn_fwd(qkv, lay, mask, H, 0.125, drop)
+                t_f = timed(lambda: ops.attn_fwd(qkv, lay, mask, H, 0.125, drop), a.iters)
+                dq, t_b = None, float('nan')
+                if not a.no_bwd:
+                    dq = ops.attn_bwd(qkv, out, dout, lay, mask, lse, H, 0.125, drop)
+                    t_b = timed(lambda: ops.attn_bwd(qkv, out, dout, lay, mask, lse, H, 0.125, drop), a.iters)
+                res[tc] = (out.float(), lse, None if dq is None else dq.float(), t_f, t_b)
+            o0, l0, g0, tf0, tb0 = res['0']
+            o1, l1, g1, tf1, tb1 = res[a.tc]
+            desc = lay.seq_desc.long()
+            nlen = (desc[:, 1] + desc[:, 3])[:, None, None]
+            fin = (torch.arange(lay.max_seq_len, device=dev)[None, None, :] < nlen).expand(lay.num_seqs, H, lay.max_seq_len).reshape(-1)
+            fin = fin & torch.isfinite(l0)
+            line = (f'{name:15s} drop={"y" if drop else "n"}  fwd {tf0:7.1f} -> {tf1:7.1f} us   bwd {tb0:7.1f} -> {tb1:7.1f} us   '
+                    f'max|dout| {float((o0 - o1).abs().max()):.3e} (ref max {float(o0.abs().max()):.2f})  '
+                    f'max|dlse| {float((l0[fin] - l1[fin]).abs().max()):.3e}  nan {int(torch.isnan(o1).sum())}')
+            if g0 is not None:
+                line += f'  max|dgrad| {float((g0 - g1).abs().max()):.3e} (ref max {float(g0.abs().max()):.2f})'
+            print(line, flush=True)
+    os.environ['MOME_ATTN_TC'] = '0'
+
+
+if __name__ == '__main__':
+    main()
