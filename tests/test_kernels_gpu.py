@@ -363,11 +363,22 @@ def test_attention_tcgen05_forward_matches_mma_sync(drop, mask_kind, monkeypatch
     assert (o0.float() - o1.float()).abs().max() <= 2.0 ** -6      # one bf16 ulp at |x| < 4
     assert rel_err(o1, o0) < 4e-3
     assert (l0 - l1).abs().max() < 1e-4
-    # and the mma.sync backward takes the tcgen05 forward's outputs
+    # backward: either backward takes either forward's outputs, and the two backward paths agree
     dout = _rand(lay.tokens, 64 * H, dtype=torch.bfloat16, seed=12)
-    g0 = ops.attn_bwd(qkv, o0, dout, lay, mask, l0, H, 0.125, dr)
+    valid = torch.zeros(lay.tokens, dtype=torch.bool, device=_dev())
+    for (s0, n0_, s1, n1_) in lay.seq_desc.tolist():
+        valid[s0:s0 + n0_] = True
+        valid[s1:s1 + n1_] = True
+    grads = {}
+    for bwd in ('0', '1'):
+        monkeypatch.setenv('MOME_ATTN_TC_BWD', bwd)
+        n0 = L.lib().mome_launch_count()
+        grads[bwd] = ops.attn_bwd(qkv, o0, dout, lay, mask, l0, H, 0.125, dr)
+        assert L.lib().mome_launch_count() == n0 + 2     # dq + dkv kernels, or delta + fused tcgen05 kernel
+    assert torch.isfinite(grads['1'][valid].float()).all()
+    assert rel_err(grads['1'][valid], grads['0'][valid]) < 1e-2
     g1 = ops.attn_bwd(qkv, o1, dout, lay, mask, l1, H, 0.125, dr)
-    assert rel_err(g1, g0) < 1e-2
+    assert rel_err(g1[valid], grads['0'][valid]) < 1e-2
 
 
 def test_attention_no_mask_pointer():

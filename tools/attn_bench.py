@@ -37,6 +37,7 @@ def main():
     ap.add_argument('--drop', type=float, default=0.1)
     ap.add_argument('--tc', default='1', help='MOME_ATTN_TC value to compare against the mma.sync kernels')
     ap.add_argument('--mask', default='ones', choices=['ones', 'random', 'pad'], help='key mask: all ones (the bench), 10 %% random zeros, or padded text (lengths 8..40)')
+    ap.add_argument('--tc-bwd', action='store_true', help='also select the experimental tcgen05 backward (MOME_ATTN_TC_BWD=1) for the second variant')
     ap.add_argument('--only', default='', help='substring of the layout name to run')
     a = ap.parse_args()
     B, H, T, P = a.batch, a.heads, 40, 197
@@ -62,6 +63,7 @@ def main():
             res = {}
             for tc in ('0', a.tc):
                 os.environ['MOME_ATTN_TC'] = tc
+                os.environ['MOME_ATTN_TC_BWD'] = '1' if (a.tc_bwd and tc != '0') else '0'
                 out, lse = ops.attn_fwd(qkv, lay, mask, H, 0.125, drop)
                 t_f = timed(lambda: ops.attn_fwd(qkv, lay, mask, H, 0.125, drop), a.iters)
                 dq, t_b = None, float('nan')
@@ -82,6 +84,7 @@ def main():
                 line += f'  max|dgrad| {float((g0 - g1).abs().max()):.3e} (ref max {float(g0.abs().max()):.2f})'
             print(line, flush=True)
     os.environ['MOME_ATTN_TC'] = '0'
+    os.environ['MOME_ATTN_TC_BWD'] = '0'
 
 
 if __name__ == '__main__':
