@@ -57,19 +57,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// rows [t0, t0 + rows) of the sequence (rows % 16 == 0), 64 bf16 at column offset folded into `gbase`
-// -> SWIZZLE_128B tile (16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)); rows past n are zero filled
-__device__ __forceinline__ void load_rows_async(uint8_t* tile, const __nv_bfloat16* gbase, long long ld, const Seq& sd, int n, int t0,
-                                                int rows) {
-  const int r0 = threadIdx.x >> 3, ch = threadIdx.x & 7;
-  const uint32_t dst = r0 * 128 + ((ch ^ (r0 & 7)) << 4);  // (r0 + 16 i) & 7 == r0 & 7
-  for (int i = 0; r0 + 16 * i < rows; ++i) {
-    const int t = t0 + r0 + 16 * i;
-    const bool valid = t < n;
-    cp_async_16(tile + dst + i * 2048, gbase + seq_row(sd, valid ? t : 0) * ld + ch * 8, valid);
-  }
-}
-
 // Forward: persistent and warp-specialised. One CTA per SM walks over (sequence, head) items;
 // both 128-query tiles of an item share one load of K and V, the probabilities never touch shared memory.
 //
