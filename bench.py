@@ -9,6 +9,8 @@ sequences), backward, and a fused AdamW update. Workload = BASELIN
 (VLMo-base, global batch 1024 on 8 GPUs => 128 samples per GPU; weak scaling).
 
 Prints ONE JSON line (rank 0). See the module docstring of each helper for what every key means.
+`config.attention` names the attention kernels that were measured: before the run a child process checks the
+tcgen05 attention kernels against the mma.sync ones on this GPU at the step's sizes (attention_preflight).
 """
 import argparse
 import json
@@ -174,6 +176,30 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------- product arm
+def attention_preflight(batch, device):
+    """The tcgen05 attention kernels are the default for the step's layouts; before the measurement a child process
+    runs them against the mma.sync kernels on this GPU at the step's sizes (tools/attn_bench.py --check: outputs,
+    log-sum-exp and gradients, with and without dropout). A child, because a faulting kernel poisons its CUDA context.
+    If it fails, this run measures the mma.sync kernels instead and says so in `config.attention`."""
+    if 'MOME_ATTN_TC' in os.environ or 'MOME_ATTN_TC_BWD' in os.environ:
+        return {'fwd': 'env MOME_ATTN_TC=' + os.environ.get('MOME_ATTN_TC', ''), 'bwd': 'env MOME_ATTN_TC_BWD=' + os.environ.get('MOME_ATTN_TC_BWD', '')}
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'attn_bench.py')
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT')}
+    try:
+        r = subprocess.run([sys.executable, tool, '--check', '--tc-bwd', '--iters', '1', '--batch', str(2 * batch), '--device', str(device)],
+                           env=env, capture_output=True, text=True, timeout=180)
+        ok = r.returncode == 0 and 'CHECK OK' in r.stdout
+        detail = '' if ok else (r.stdout[-300:] + r.stderr[-300:])
+    except Exception as e:  # timeout, missing tool
+        ok, detail = False, repr(e)
+    if ok:
+        return {'fwd': 'tcgen05', 'bwd': 'tcgen05', 'preflight': 'ok'}
+    os.environ['MOME_ATTN_TC'] = '0'
+    os.environ['MOME_ATTN_TC_BWD'] = '0'
+    print('bench: attention pre-flight failed, measuring the mma.sync attention kernels: ' + detail, file=sys.stderr, flush=True)
+    return {'fwd': 'mma.sync', 'bwd': 'mma.sync', 'preflight': 'failed'}
+
+
 def run_mome(args):
     import torch
     import torch.distributed as dist
@@ -184,6 +210,7 @@ def run_mome(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    attention = attention_preflight(args.batch, local) if args.precision == 'bf16' else {'fwd': 'simt fp32', 'bwd': 'simt fp32'}
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -327,7 +354,7 @@ def run_mome(args):
                                f'{world * B} = {B}/GPU x {world})', 'per_gpu_batch': B, 'global_batch': world * B,
                    'img': 224, 'text_len': 40, 'lengths': args.lengths, 'parallelism': f'dp{world}',
                    'dropout': {'drop_rate': cfg.model.drop_rate, 'attn_drop_rate': cfg.model.attn_drop_rate,
-                               'drop_path_rate': cfg.model.drop_path_rate}, 'cuda_graph': bool(graph is not None),
+                               'drop_path_rate': cfg.model.drop_path_rate}, 'cuda_graph': bool(graph is not None), 'attention': attention,
                    'l2': 'per-step working set (~50 GB of activations) far exceeds the 126 MB L2; no flush needed'},
         'samples_per_sec_per_gpu': value / world,
         'model_tflops_per_gpu': fps * B / (ms_step * 1e-3) / 1e12,

@@ -38,11 +38,15 @@ def main():
     ap.add_argument('--tc', default='1', help='MOME_ATTN_TC value to compare against the mma.sync kernels')
     ap.add_argument('--mask', default='ones', choices=['ones', 'random', 'pad'], help='key mask: all ones (the bench), 10 %% random zeros, or padded text (lengths 8..40)')
     ap.add_argument('--tc-bwd', action='store_true', help='also select the experimental tcgen05 backward (MOME_ATTN_TC_BWD=1) for the second variant')
+    ap.add_argument('--check', action='store_true', help='exit 1 if the two variants disagree (used by bench.py as a pre-flight check)')
+    ap.add_argument('--device', type=int, default=0)
     ap.add_argument('--only', default='', help='substring of the layout name to run')
     a = ap.parse_args()
     B, H, T, P = a.batch, a.heads, 40, 197
     d = 64 * H
-    dev = torch.device('cuda')
+    torch.cuda.set_device(a.device)
+    dev = torch.device('cuda', a.device)
+    bad = []
     layouts = [('fused 40+197', ops.fused_layout(B, T, P, dev)), ('split 40 / 197', ops.split_layout(B, T, P, dev)),
                ('image 197', ops.single_layout(B, P, 'v', dev)), ('text 40', ops.single_layout(B, T, 'l', dev))]
     seed = torch.tensor([1234], dtype=torch.int32, device=dev)
@@ -83,8 +87,17 @@ def main():
             if g0 is not None:
                 line += f'  max|dgrad| {float((g0 - g1).abs().max()):.3e} (ref max {float(g0.abs().max()):.2f})'
             print(line, flush=True)
+            # pre-flight criteria: finite, within two bf16 ulps of the mma.sync result at these magnitudes, same log-sum-exp
+            ok = int(torch.isnan(o1).sum()) == 0 and float((o0 - o1).abs().max()) <= 2.0 ** -5 and float((l0[fin] - l1[fin]).abs().max()) < 1e-3
+            if g0 is not None:
+                ok = ok and bool(torch.isfinite(g1).all()) and float((g0 - g1).abs().max()) <= 2.0 ** -4 * max(1.0, float(g0.abs().max()) / 4)
+            if not ok:
+                bad.append((name, bool(drop)))
     os.environ['MOME_ATTN_TC'] = '0'
     os.environ['MOME_ATTN_TC_BWD'] = '0'
+    if a.check:
+        print('CHECK ' + ('FAILED ' + repr(bad) if bad else 'OK'), flush=True)
+        sys.exit(1 if bad else 0)
 
 
 if __name__ == '__main__':
