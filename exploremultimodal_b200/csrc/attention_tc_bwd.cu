@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   }
 }
 
-template <bool DROP>
+// EARLY_S (experimental, MOME_ATTN_TC_BWD=2): S / dP of the next block of the item are issued before the accumulate
+// MMAs of the current one, so the P / dS group works on block b + 1 while the tensor core finishes block b.
+template <bool DROP, bool EARLY_S>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -267,22 +269,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           for (int i = 0; i < nt; ++i, ++blk) {
             const int kq = min(kTile, ((n - i * kTile) + 15) & ~15);  // query rows of the tile
             // ---- S = Q_i K_j^T, dP = dO_i V_j^T (the group has consumed the previous S / dP: pds_full was waited for)
-            {
-              const uint32_t idesc = umma_idesc_bf16(kTile, kk, false, false);
+            auto issue_sdp = [&](int jj, int ii) {
+              const int kkk = min(kTile, ((n - jj * kTile) + 15) & ~15);
+              const uint32_t idesc = umma_idesc_bf16(kTile, kkk, false, false);
 #pragma unroll
               for (int c = 0; c < kHd / 16; ++c)
-                umma_bf16(tmem_base + kColS, umma_smem_desc(sQ + i * 16384 + c * 32, 0, 1024), umma_smem_desc(sK + j * 16384 + c * 32, 0, 1024),
+                umma_bf16(tmem_base + kColS, umma_smem_desc(sQ + ii * 16384 + c * 32, 0, 1024), umma_smem_desc(sK + jj * 16384 + c * 32, 0, 1024),
                           idesc, c > 0 ? 1u : 0u);
 #pragma unroll
               for (int c = 0; c < kHd / 16; ++c)
-                umma_bf16(tmem_base + kColDP, umma_smem_desc(sG + i * 16384 + c * 32, 0, 1024), umma_smem_desc(sV + j * 16384 + c * 32, 0, 1024),
+                umma_bf16(tmem_base + kColDP, umma_smem_desc(sG + ii * 16384 + c * 32, 0, 1024), umma_smem_desc(sV + jj * 16384 + c * 32, 0, 1024),
                           idesc, c > 0 ? 1u : 0u);
               umma_commit(sdp_full);
-            }
+            };
+            if (!EARLY_S || (j == 0 && i == 0)) issue_sdp(j, i);
             mbar_wait_park(pds_full, blk & 1);
             if (i == 0 && (j > 0 || k > 0)) mbar_wait_park(dkv_free, (jcount & 1) ^ 1);  // previous dK / dV drained
             if (i == 0 && j == 0 && k > 0) mbar_wait_park(dq_free, (k & 1) ^ 1);          // previous item's dQ drained
             tcgen05_fence_after();
+            if (EARLY_S) {  // next block of this item, in visiting order (i fastest)
+              const int ni = i + 1 < nt ? i + 1 : 0, nj = i + 1 < nt ? j : j + 1;
+              if (nj < nt) issue_sdp(nj, ni);
+            }
             {
               // dV_j += P^T dO_i, dK_j += dS^T Q_i: A = [q][keys] tile read MN-major (M = keys), K = query rows
               const uint32_t idesc_t = umma_idesc_bf16(kTile, kHd, true, true);
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           const float L = Lr[i], D = Dr[i];
           const uint32_t drow = attn_drop_row(s, H, h, p.max_seq_len, q) + ((j * kTile + half * 64) >> 1);
           mbar_wait_park(sdp_full, blk & 1);
-          if (blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // the previous block's MMAs are done with the P / dS tiles
+          if (!EARLY_S && blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // the previous block's MMAs are done with the P / dS tiles
           __syncwarp();
           tcgen05_fence_after();
 #pragma unroll 1
@@ -380,6 +388,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
               pp[e] = pack_bf16(pd0, pd1);
               ds[e] = pack_bf16(s0, s1);
             }
+            if (EARLY_S && c == 0 && blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // first store of the block
             // keys c 16 + [0, 16) of this thread's 64: 16-byte chunks 2 c and 2 c + 1 of the row segment
             *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
             *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
@@ -472,11 +481,15 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   MOME_REQUIRE(max_seq_len <= kMaxKeys, "attn_bwd_tc: max_seq_len %d > %d", max_seq_len, kMaxKeys);
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in(attn_bwd_tc_kernel<false>, kBwdSmem, "attn_bwd_tc");
-    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true>, kBwdSmem, "attn_bwd_tc");
+    int rc = opt_in(attn_bwd_tc_kernel<false, false>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, false>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<false, true>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, true>, kBwdSmem, "attn_bwd_tc");
     if (rc != MOME_OK) return rc;
     configured = true;
   }
+  const char* variant = getenv("MOME_ATTN_TC_BWD");
+  const bool early_s = variant != nullptr && variant[0] == '2';
   BwdParams p;
   const int64_t d = static_cast<int64_t>(H) * kHd, d3 = 3 * d;
   int rc = tma_encode_bf16_2d(&p.qkv32, qkv, d3, tokens, d3, kHd, 32);
@@ -504,10 +517,11 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   rc = check_launch("attn_delta");
   if (rc != MOME_OK) return rc;
   const int grid = std::min(p.num_items, sm_count());
-  if (drop_seed != nullptr && drop_p > 0.f)
-    attn_bwd_tc_kernel<true><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
-  else
-    attn_bwd_tc_kernel<false><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
+  const bool drop = drop_seed != nullptr && drop_p > 0.f;
+  if (drop && early_s) attn_bwd_tc_kernel<true, true><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
+  else if (drop) attn_bwd_tc_kernel<true, false><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
+  else if (early_s) attn_bwd_tc_kernel<false, true><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
+  else attn_bwd_tc_kernel<false, false><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
   return check_launch("attn_bwd_tc");
 }
 
