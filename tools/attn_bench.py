@@ -37,7 +37,8 @@ def main():
     ap.add_argument('--drop', type=float, default=0.1)
     ap.add_argument('--tc', default='1', help='MOME_ATTN_TC value to compare against the mma.sync kernels')
     ap.add_argument('--mask', default='ones', choices=['ones', 'random', 'pad'], help='key mask: all ones (the bench), 10 %% random zeros, or padded text (lengths 8..40)')
-    ap.add_argument('--tc-bwd', action='store_true', help='also select the experimental tcgen05 backward (MOME_ATTN_TC_BWD=1) for the second variant')
+    ap.add_argument('--tc-bwd', nargs='?', const='1', default=None,
+                    help='MOME_ATTN_TC_BWD value for the second variant (1: tcgen05 backward, 2: its EARLY_S scheduling); default: mma.sync backward in both')
     ap.add_argument('--check', action='store_true', help='exit 1 if the two variants disagree (used by bench.py as a pre-flight check)')
     ap.add_argument('--device', type=int, default=0)
     ap.add_argument('--only', default='', help='substring of the layout name to run')
@@ -67,7 +68,7 @@ def main():
             res = {}
             for tc in ('0', a.tc):
                 os.environ['MOME_ATTN_TC'] = tc
-                os.environ['MOME_ATTN_TC_BWD'] = '1' if (a.tc_bwd and tc != '0') else '0'
+                os.environ['MOME_ATTN_TC_BWD'] = a.tc_bwd if (a.tc_bwd and tc != '0') else '0'
                 out, lse = ops.attn_fwd(qkv, lay, mask, H, 0.125, drop)
                 t_f = timed(lambda: ops.attn_fwd(qkv, lay, mask, H, 0.125, drop), a.iters)
                 dq, t_b = None, float('nan')
