@@ -148,7 +148,8 @@ int mome_gemm(const MomeGemmArgs* args, void* stream);
  * reference: vlmo.py:79-95 (split heads, q k^T * scale, masked_fill(~mask, -inf), softmax, @ v,
  * merge heads). qkv is the [tokens, 3*d] output of the qkv GEMM (column = s*d + h*64 + e).
  * A sequence is up to two row ranges of the packed buffer ([text | image] after the fusion layer,
- * one range before it): seq_desc[4*s + {0,1,2,3}] = {start0, len0, start1, len1}.
+ * one range before it): seq_desc[4*s + {0,1,2,3}] = {start0, len0, start1, len1}, len0 + len1 >= 1 (no empty
+ * sequences) and <= max_seq_len.
  * key_mask[row] = 1 keeps the key, 0 excludes it; query rows are never masked. head_dim is 64.
  * drop_seed (device scalar, NULL = off) / drop_salt / drop_p: dropout on the attention probabilities (vlmo.py:93),
  * bf16 path only; the backward must be given the same three values (masks are regenerated, csrc/dropout.cuh). */
