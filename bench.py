@@ -10,7 +10,8 @@ sequences), backward, and a fused AdamW update. Workload = BASELIN
 
 Prints ONE JSON line (rank 0). See the module docstring of each helper for what every key means.
 `config.attention` names the attention kernels that were measured: before the run a child process checks the
-tcgen05 attention kernels against the mma.sync ones on this GPU at the step's sizes (attention_preflight).
+tcgen05 attention kernels against the mma.sync ones on this GPU at the step's sizes (attention_preflight; setting
+MOME_ATTN_TC or MOME_ATTN_TC_BWD in the environment skips it and pins the choice, e.g. under ncu).
 """
 import argparse
 import json
