@@ -2,7 +2,7 @@
 take minutes at these sizes) plus a thin oracle cross-check on a slice:
 
   * VLMo-base, 128 samples (configs[1] per-GPU share): attention rows are convex combinations (V = 1 -> out = 1,
-    masked keys carry no weight), GEMM linearity / transposition identities between the forward, dgrad and
+    masked keys carry no weight), the attention backward conserves dO (sum of dV over keys = sum of dO over queries), GEMM linearity / transposition identities between the forward, dgrad and
     wgrad operand-major variants, LayerNorm output statistics, gradient-accumulation idempotence;
   * VLMo-large width (d = 1024, 16 heads, gamma init 1e-5) and the VQA-480 sequence length (941 tokens),
     2 layers, against the oracle.
@@ -44,6 +44,36 @@ def test_attention_rows_are_convex_combinations_full_size():
     qkv[:, 2 * d:] = (1 - key_mask.float())[:, None].to(torch.bfloat16)
     out, _ = ops.attn_fwd(qkv, lay, key_mask, H, 0.125)
     assert out.float().abs().max() == 0.0
+
+
+def _per_sequence_sum(x, B, T, P):
+    """x [B*(T+P), c] in the packed layout (text rows first, then image rows) -> [B, c] sums over each sequence."""
+    return x[:B * T].reshape(B, T, -1).sum(1) + x[B * T:].reshape(B, P, -1).sum(1)
+
+
+def test_attention_backward_conserves_dout_full_size():
+    """Same 128 x [40 | 197] x 12-head problem, backward: softmax rows sum to one, so summed over the keys of a
+    sequence dV equals dO summed over its queries (per head and channel), whatever Q, K and the key mask are;
+    masked keys receive exactly zero dK and dV; every gradient is finite."""
+    L, ops = _mods()
+    B, T, P, H = 128, 40, 197, 12
+    d = 64 * H
+    dev = torch.device('cuda')
+    lay = ops.fused_layout(B, T, P, dev)
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(B * (T + P), 3 * d, generator=g).to(dev).to(torch.bfloat16)
+    dout = torch.randn(B * (T + P), d, generator=g).to(dev).to(torch.bfloat16)
+    lens = torch.randint(8, T + 1, (B,), generator=g)
+    txt_mask = (torch.arange(T)[None, :] < lens[:, None]).to(torch.uint8)
+    key_mask = torch.cat([txt_mask.reshape(-1), torch.ones(B * P, dtype=torch.uint8)]).to(dev)
+    out, lse = ops.attn_fwd(qkv, lay, key_mask, H, 0.125)
+    dqkv = ops.attn_bwd(qkv, out, dout, lay, key_mask, lse, H, 0.125)
+    assert torch.isfinite(dqkv.float()).all()
+    dv = dqkv[:, 2 * d:].float()
+    assert rel_err(_per_sequence_sum(dv, B, T, P), _per_sequence_sum(dout.float(), B, T, P)) < 1e-2
+    masked = key_mask == 0
+    assert int(masked.sum()) > 0
+    assert dqkv[masked][:, d:].float().abs().max() == 0.0
 
 
 def test_gemm_major_variants_agree_full_size():
