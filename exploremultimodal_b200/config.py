@@ -4,7 +4,7 @@ The reference composes its config with Hydra from conf/config.yaml + conf/model/
 conf/train/*.yaml (reference main.py:86); the model only ever uses attribute access and
 `hasattr` on it (reference models/vlmo/vlmo_module.py:16-146), so a SimpleNamespace tree with
 the same field names is a drop-in. Values below are the ones in conf/model/vlmo_{base,large,
-debug}.yaml and conf/train/pretrain_mum.yaml / finetune_vqa.yaml; `mlp_ratio` is an int
+huge,small,tiny,debug}.yaml and conf/train/pretrain_mum.yaml / finetune_vqa.yaml; `mlp_ratio` is an int
 (the YAML's `4.` is numerically the same).
 """
 from types import SimpleNamespace
@@ -21,6 +21,11 @@ MODEL_ZOO = {
     'vlmo_base': dict(embed_dim=768, depth=12, num_heads=12, init_values=0.1, fusion_layer=6),
     # conf/model/vlmo_large.yaml
     'vlmo_large': dict(embed_dim=1024, depth=24, num_heads=16, init_values=1e-5, fusion_layer=12),
+    # conf/model/vlmo_huge.yaml (same geometry as large in the reference)
+    'vlmo_huge': dict(embed_dim=1024, depth=24, num_heads=16, init_values=1e-5, fusion_layer=12),
+    # conf/model/vlmo_small.yaml, vlmo_tiny.yaml
+    'vlmo_small': dict(embed_dim=384, depth=12, num_heads=6, init_values=0.1, fusion_layer=6),
+    'vlmo_tiny': dict(embed_dim=192, depth=12, num_heads=3, init_values=0.1, fusion_layer=6, itc_dim=64),
     # conf/model/vlmo_debug.yaml
     'vlmo_debug': dict(embed_dim=96, depth=2, num_heads=3, init_values=0.1, fusion_layer=1,
                        itc_dim=32),

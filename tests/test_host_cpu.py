@@ -157,6 +157,37 @@ def test_phase_surgery_removes_unused_experts():
         assert 'v' in blk.mlp and 'l' in blk.mlp
 
 
+# conf/model/*.yaml of the reference: (embed_dim, depth, num_heads, init_values, fusion_layer, itc_dim); everything else
+# is common: vocab 30522, 40 text tokens, 224 / 16 patches, mlp_ratio 4, qkv_bias, 0.1 / 0.1 / 0.1 drop rates, itc_temp 0.07
+REFERENCE_MODELS = {
+    'vlmo_base': (768, 12, 12, 0.1, 6, 256),
+    'vlmo_large': (1024, 24, 16, 1e-5, 12, 256),
+    'vlmo_huge': (1024, 24, 16, 1e-5, 12, 256),
+    'vlmo_small': (384, 12, 6, 0.1, 6, 256),
+    'vlmo_tiny': (192, 12, 3, 0.1, 6, 64),
+    'vlmo_debug': (96, 2, 3, 0.1, 1, 32),
+}
+
+
+def test_model_zoo_matches_reference_yaml():
+    import os
+    for name, (dim, depth, heads, init, fusion, itc_dim) in REFERENCE_MODELS.items():
+        m = make_config(name).model
+        assert (m.embed_dim, m.depth, m.num_heads, m.init_values, m.fusion_layer, m.itc_dim) == (dim, depth, heads, init, fusion, itc_dim), name
+        assert (m.vocab_size, m.max_text_len, m.img_size, m.patch_size, m.in_chans, m.mlp_ratio, m.qkv_bias) == (30522, 40, 224, 16, 3, 4, True)
+        assert (m.drop_rate, m.attn_drop_rate, m.drop_path_rate, m.itc_temp) == (0.1, 0.1, 0.1, 0.07)
+        ref = f'/root/reference/conf/model/{name}.yaml'   # only in the build container; the table above is what travels
+        if os.path.exists(ref):
+            import yaml
+            y = yaml.safe_load(open(ref))
+            for k in ('embed_dim', 'depth', 'num_heads', 'fusion_layer', 'itc_dim', 'vocab_size', 'max_text_len', 'img_size',
+                      'patch_size', 'drop_rate', 'attn_drop_rate', 'drop_path_rate', 'itc_temp', 'qkv_bias'):
+                assert getattr(m, k) == y[k], (name, k)
+            assert float(m.init_values) == float(y['init_values']) and float(m.mlp_ratio) == float(y['mlp_ratio'])
+    p = make_config('vlmo_base', parity=True).model
+    assert (p.drop_rate, p.attn_drop_rate, p.drop_path_rate) == (0.0, 0.0, 0.0)
+
+
 def test_unsupported_objectives_fail_loudly():
     import pytest
     with pytest.raises(NotImplementedError):
