@@ -376,9 +376,9 @@ def test_attention_tcgen05_forward_matches_mma_sync(drop, mask_kind, monkeypatch
         grads[bwd] = ops.attn_bwd(qkv, o0, dout, lay, mask, l0, H, 0.125, dr)
         assert L.lib().mome_launch_count() == n0 + 2     # dq + dkv kernels, or delta + fused tcgen05 kernel
     assert torch.isfinite(grads['1'][valid].float()).all()
-    assert rel_err(grads['1'][valid], grads['0'][valid]) < 1e-2
+    assert rel_err(grads['1'][valid], grads['0'][valid]) < BF16_TOL * 2   # two bf16 pipelines against each other
     g1 = ops.attn_bwd(qkv, o1, dout, lay, mask, l1, H, 0.125, dr)
-    assert rel_err(g1[valid], grads['0'][valid]) < 1e-2
+    assert rel_err(g1[valid], grads['0'][valid]) < BF16_TOL * 2
 
 
 def test_attention_no_mask_pointer():
