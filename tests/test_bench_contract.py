@@ -26,3 +26,15 @@ def test_reference_arm_prints_the_contract_line():
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['unit'] == 'samples/s' and cb['value'] == d['value'] and cb['sample']
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == 'samples/s' and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: rank 0 alone runs the CPU port and prints the line, the other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29643', os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                        '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
