@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 K_MAJOR, MN_MAJOR = 0, 1
 MAX_GROUPS = 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class GemmGroup(C.Structure):
@@ -56,7 +56,7 @@ class BlockArgs(C.Structure):
                 + [('group', BlockGroup * MAX_GROUPS)]
                 + [(n, C.c_void_p) for n in ('x', 'h', 'mean1', 'rstd1', 'qkv', 'o', 'lse', 'br1', 'x1', 'h2', 'mean2',
                                              'rstd2', 'gp', 'u', 'br2', 'x2', 'dx2', 'dx', 'dgamma_1', 'dgamma_2',
-                                             'dn1w', 'dn1b', 'dn2w', 'dn2b', 'dqkv_bias', 'dproj_b', 'dw_qkv',
+                                             'dn1w', 'dn1b', 'dn2w', 'dn2b', 'dq_bias', 'dv_bias', 'dproj_b', 'dw_qkv',
                                              'dw_proj', 's_dbr2', 's_dh2', 's_dbr1', 's_do', 's_dh', 's_dz', 's_dqkv',
                                              's_dx1', 's_delta', 'ws')]
                 + [('ws_bytes', C.c_size_t), ('drop_seed', C.c_void_p), ('row_sample', C.c_void_p),

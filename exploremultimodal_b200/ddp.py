@@ -6,18 +6,35 @@ libmome's weight-gradient kernels accumulate straight into those views: `fused_g
 called several times per step (5 backbone passes share its weights); when the backward of its LAST call of the
 step has run, its buffer is final and is all-reduced (mean) on a side stream while the remaining backward keeps
 the compute stream busy. Parameters outside the blocks (embeddings, heads) are reduced at the end. No copies:
-NCCL works in place on the flat buffers. Everything is stream ordered (capturable in a CUDA graph)."""
+NCCL works in place on the flat buffers. Everything is stream ordered (capturable in a CUDA graph).
+
+Contract with the training loop:
+  * clear gradients with `optimizer.zero_grad(set_to_none=False)` (or `GradSync.zero_grad()`): the `.grad`
+    tensors must stay the views into the flat buffers. If something replaced them anyway (PyTorch's default
+    `set_to_none=True`), `finish()` notices, copies the stray gradients back into the flat buffer, re-binds the
+    views and reduces that buffer then — slower, never silently wrong;
+  * call `finish()` after `backward()` and before `optimizer.step()`. It also reduces every block whose
+    "last backward" hook did not fire in this step (a forward without backward, a skipped loss) and resets
+    the per-block counters, so one irregular step cannot switch synchronisation off for the following ones.
+`reduce_dtype='bf16'` halves the NVLink bytes: the flat buffer is cast to bf16, all-reduced (NCCL accumulates
+bf16 sums in fp32 internally per hop) and cast back; default fp32 = bit-for-bit the reference's DDP arithmetic."""
 import torch
 import torch.distributed as dist
 
 
 class GradSync:
 
-    def __init__(self, model, world):
+    def __init__(self, model, world, reduce_dtype='fp32'):
+        assert reduce_dtype in ('fp32', 'bf16')
         self.world = world
+        self.reduce_dtype = reduce_dtype
         self.comm = torch.cuda.Stream() if world > 1 else None
         in_block = set()
+        self.blocks = []
         self.block_flat = []
+        self._views = []          # (param, view into a flat buffer)
+        self._view_of = {}        # id(param) -> that view
+        self._fired = set()       # ids of blocks whose buffer was reduced in this step
         for blk in model.transformer.blocks:
             ps = [p for p in blk.parameters() if p.requires_grad]
             flat = self._flatten(ps)
@@ -25,27 +42,79 @@ class GradSync:
             blk.fused_grad_accumulation = True
             blk.grads_ready_hook = self._on_block_ready if world > 1 else None
             blk._flat_grad = flat
+            blk._pending_bwd = 0
+            self.blocks.append((blk, ps))
             self.block_flat.append(flat)
-        rest = [p for p in model.parameters() if p.requires_grad and id(p) not in in_block]
-        self.rest_flat = self._flatten(rest)
+        self.rest = [p for p in model.parameters() if p.requires_grad and id(p) not in in_block]
+        self.rest_flat = self._flatten(self.rest)
 
-    @staticmethod
-    def _flatten(ps):
+    def _flatten(self, ps):
+        if not ps:
+            return None
         flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
         off = 0
         for p in ps:
-            p.grad = flat[off:off + p.numel()].view_as(p)
+            view = flat[off:off + p.numel()].view_as(p)
+            p.grad = view
+            self._views.append((p, view))
+            self._view_of[id(p)] = view
             off += p.numel()
         return flat
 
+    def zero_grad(self):
+        for flat in self.block_flat + [self.rest_flat]:
+            if flat is not None:
+                flat.zero_()
+        for p, view in self._views:
+            p.grad = view
+
+    def _all_reduce(self, flat):
+        if self.reduce_dtype == 'bf16':
+            low = flat.to(torch.bfloat16)
+            dist.all_reduce(low, op=dist.ReduceOp.AVG)
+            flat.copy_(low)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
     def _on_block_ready(self, blk):
+        if blk._flat_grad is None:
+            return
+        self._fired.add(id(blk))
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
-            dist.all_reduce(blk._flat_grad, op=dist.ReduceOp.AVG)
+            self._all_reduce(blk._flat_grad)
+
+    def _rebind(self, ps):
+        """True if any .grad of `ps` had left its flat buffer (its values are copied back in)."""
+        moved = False
+        for p in ps:
+            view = self._view_of[id(p)]
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+                moved = True
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+                p.grad = view
+                moved = True
+        return moved
 
     def finish(self):
         """Call after backward, before the optimizer step."""
+        for blk, ps in self.blocks:
+            moved = self._rebind(ps) if ps else False
+            late = blk._pending_bwd != 0 or id(blk) not in self._fired or moved
+            blk._pending_bwd = 0
+            if self.world > 1 and late and blk._flat_grad is not None:
+                if id(blk) in self._fired:      # a stale buffer went out earlier: wait for it before reducing again
+                    torch.cuda.current_stream().wait_stream(self.comm)
+                self._all_reduce(blk._flat_grad)
+        self._fired.clear()
+        if self.rest:
+            self._rebind(self.rest)
         if self.world == 1:
             return
-        dist.all_reduce(self.rest_flat, op=dist.ReduceOp.AVG)
+        if self.rest_flat is not None:
+            self._all_reduce(self.rest_flat)
         torch.cuda.current_stream().wait_stream(self.comm)

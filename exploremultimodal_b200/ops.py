@@ -302,7 +302,7 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     for i, (s, n, route) in enumerate(lay.groups):
         dw1, db1 = buf(('mlp', route, 0), hid, d), buf(('mlp', route, 1), hid)
         dw2, db2 = buf(('mlp', route, 2), d, hid), buf(('mlp', route, 3), d)
-        part = torch.zeros((n + 31) // 32, hid, **f32)
+        part = torch.empty((n + 31) // 32, hid, **f32)  # the DGELU epilogue writes every slab of every column once
         grads[('mlp', route)] = (dw1, db1, dw2, db2)
         g = a.group[i]
         g.dw1, g.db1, g.dw2, g.db2, g.colsum_part = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), part.data_ptr()
@@ -311,12 +311,14 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     dgamma2 = buf('gamma_2', d) if has_gamma else None
     dn1w, dn1b, dn2w, dn2b = buf('n1w', d), buf('n1b', d), buf('n2w', d), buf('n2b', d)
     dproj_b, dw_proj, dw_qkv = buf('proj_b', d), buf('w_proj', d, d), buf('w_qkv', 3 * d, d)
-    dqkv_bias = torch.zeros(3 * d, **f32) if p.qkv_bias is not None else None  # [dq_bias | unused k part | dv_bias]
+    dq_bias = buf('q_bias', d) if p.qkv_bias is not None else None
+    dv_bias = buf('v_bias', d) if p.qkv_bias is not None else None
     dx = torch.empty_like(x)
     a.dx2, a.dx = dx2.data_ptr(), dx.data_ptr()
     a.dgamma_1, a.dgamma_2 = L.ptr(dgamma1), L.ptr(dgamma2)
     a.dn1w, a.dn1b, a.dn2w, a.dn2b = dn1w.data_ptr(), dn1b.data_ptr(), dn2w.data_ptr(), dn2b.data_ptr()
-    a.dqkv_bias, a.dproj_b, a.dw_qkv, a.dw_proj = L.ptr(dqkv_bias), dproj_b.data_ptr(), dw_qkv.data_ptr(), dw_proj.data_ptr()
+    a.dq_bias, a.dv_bias = L.ptr(dq_bias), L.ptr(dv_bias)
+    a.dproj_b, a.dw_qkv, a.dw_proj = dproj_b.data_ptr(), dw_qkv.data_ptr(), dw_proj.data_ptr()
     s_d = torch.empty(5, tokens, d, **act)       # dbr2, dh2, dbr1, do, dh
     s_dz = torch.empty(tokens, hid, **act)
     s_dqkv = torch.empty(tokens, 3 * d, **act)
@@ -327,7 +329,7 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     ws = reduce_ws(dev)
     a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
     L.check(L.lib().mome_block_bwd(C.byref(a), L.stream()), 'mome_block_bwd')
-    grads.update(gamma_1=dgamma1, gamma_2=dgamma2, n1w=dn1w, n1b=dn1b, n2w=dn2w, n2b=dn2b, qkv_bias=dqkv_bias,
+    grads.update(gamma_1=dgamma1, gamma_2=dgamma2, n1w=dn1w, n1b=dn1b, n2w=dn2w, n2b=dn2b, q_bias=dq_bias, v_bias=dv_bias,
                  w_qkv=dw_qkv, w_proj=dw_proj, proj_b=dproj_b)
     return dx, grads
 
@@ -372,16 +374,11 @@ class MomeBlockFn(torch.autograd.Function):
         if getattr(holder, 'fused_grad_accumulation', False):
             for slot, prm in zip(slots, holder._param_list(lay)):
                 if (prm is not None and prm.requires_grad and prm.grad is not None and prm.grad.dtype == torch.float32
-                        and prm.grad.is_contiguous() and slot not in ('q_bias', 'v_bias')):
+                        and prm.grad.is_contiguous()):
                     targets[slot] = prm.grad
         with torch.no_grad():
             dx, g = block_backward(dout, lay, ctx.key_mask, p, ctx.saved_tensors, targets)
-        d = dx.shape[1]
-        dqb = g['qkv_bias']
-        vals = {'gamma_1': g['gamma_1'], 'gamma_2': g['gamma_2'], 'n1w': g['n1w'], 'n1b': g['n1b'], 'n2w': g['n2w'],
-                'n2b': g['n2b'], 'q_bias': dqb[:d] if dqb is not None else None,
-                'v_bias': dqb[2 * d:] if dqb is not None else None, 'w_qkv': g['w_qkv'], 'w_proj': g['w_proj'],
-                'proj_b': g['proj_b']}
+        vals = {k: g[k] for k in MomeBlockFn.SLOTS}
         for (_, _, route) in lay.groups:
             for i, t in enumerate(g[('mlp', route)]):
                 vals[('mlp', route, i)] = t

@@ -123,8 +123,11 @@ class Pooler(nn.Module):
 
 
 class Attention(nn.Module):
-    """Parameters of reference vlmo.py:41-66. The math runs inside `Block` (fused into the block's
-    kernel sequence); calling this module on its own runs the same kernels without the residual."""
+    """Parameter container with the layout of reference vlmo.py:41-66 (`qkv.weight`, `q_bias`, `v_bias`,
+    `proj.*`). The math of reference `Attention.forward` (vlmo.py:68-98) runs inside `Block` as part of the
+    block's kernel sequence (QKV GEMM -> masked attention -> proj GEMM with the LayerScale / residual
+    epilogue); the reference never calls the attention module outside a Block (vlmo.py:189), and neither
+    does this package, so a standalone forward is deliberately not provided."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
         super().__init__()
@@ -141,6 +144,32 @@ class Attention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x, mask=None):
+        raise NotImplementedError('libmome fuses attention into Block.forward (ops.MomeBlockFn); call the Block')
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the last dimension on libmome's row kernels (fp32 in, fp32 out): the backbone's final
+    `norm` (reference vlmo.py:355,376,386,413). torch's LayerNorm backward spends 120-230 us per call in its
+    gamma/beta reduction at these shapes; mome_ln_bwd does the whole backward in one HBM pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).float().contiguous()
+        y, mean, rstd = ops.ln_fwd(x2, weight.detach().float(), bias.detach().float(), L.F32, eps)
+        ctx.save_for_backward(x2, mean, rstd, weight)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, weight = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape).float().contiguous()
+        dw = torch.zeros_like(weight, dtype=torch.float32)
+        db = torch.zeros_like(weight, dtype=torch.float32)
+        dx = ops.ln_bwd(dy2, x2, mean, rstd, weight.detach().float(), None, dw, db)
+        return dx.view(dy.shape), dw, db, None
 
 
 class _VersionedCache:
@@ -391,26 +420,44 @@ class VLMO(nn.Module):
         return x
 
     def _final_norm(self, x):
+        if x.shape[-1] % 4 == 0 and x.shape[-1] <= 1024:
+            return _LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return F.layer_norm(x, (x.shape[-1],), self.norm.weight, self.norm.bias, self.norm.eps)
 
-    def forward_interval(self, x, attn_masks, route, need_embed=True, bool_masked_pos=None, in_layer=0, out_layer=None,
-                         img_token_type_idx=1, need_norm=False):
-        """Reference vlmo.py:326-355: run blocks [in_layer, out_layer) with one route."""
+    def invalidate_weight_cache(self):
+        """Drop the derived bf16 weight copies so that the next block call rebuilds them from the fp32
+        parameters. The copies are keyed on (data_ptr, tensor version): every in-place op on a Parameter
+        (torch.optim, load_state_dict, `p.mul_()` under no_grad) bumps the version and refreshes them
+        automatically, but writes through `param.data` (DeepSpeed / apex mixed-precision optimizers, EMA
+        `p.data.copy_()`, `dist.broadcast(p.data, 0)`) do not — call this after such updates, or hook it
+        once with `attach_to_optimizer(optimizer)`."""
+        for b in self.blocks:
+            b._cache.store.clear()
+        self._pe_cache.store.clear()
+
+    def attach_to_optimizer(self, optimizer):
+        """Invalidate the weight cache after every `optimizer.step()` (for optimizers that write `.data`)."""
+        return optimizer.register_step_post_hook(lambda *_: self.invalidate_weight_cache())
+
+    def forward_interval(self, x, attn_masks, route=None, need_embed=False, bool_masked_pos=None, in_layer=None,
+                         out_layer=None, img_token_type_idx=1, need_norm=False):
+        """Reference vlmo.py:326-355: run blocks [in_layer, out_layer) with one route; returns the tensor."""
         assert route in ROUTES
         if need_embed:
             if route == 'v':
+                if attn_masks is None:
+                    attn_masks = torch.ones([x.size(0), self.patch_embed.num_patches + 1], dtype=torch.int64,
+                                            device=x.device)
                 x = self.embed_img(x, attn_masks, bool_masked_pos, img_token_type_idx)
             elif route == 'l':
                 x = self.embed_txt(x, attn_masks)
-        out_layer = len(self.blocks) if out_layer is None else out_layer
+        layers = list(range(len(self.blocks)))[in_layer:out_layer]
         B, N, d = x.shape
         lay = ops.single_layout(B, N, route, x.device)
-        key_mask = attn_masks.reshape(-1).to(torch.uint8)
-        y = self._run(x.reshape(B * N, d).float(), [(i, lay) for i in range(in_layer, out_layer)], key_mask)
+        key_mask = attn_masks.reshape(-1).to(torch.uint8) if attn_masks is not None else None
+        y = self._run(x.reshape(B * N, d).float(), [(i, lay) for i in layers], key_mask)
         y = y.view(B, N, d)
-        if need_norm:
-            y = self._final_norm(y)
-        return y, attn_masks
+        return self._final_norm(y) if need_norm else y
 
     def forward_features(self, img=None, txt=None, img_attn_masks=None, txt_attn_masks=None, bool_masked_pos=None,
                          fusion_layer=None, img_token_type_idx=1):
@@ -441,8 +488,9 @@ class VLMO(nn.Module):
         x = torch.cat([x[:B * T].view(B, T, d), x[B * T:].view(B, P, d)], 1)
         return self._final_norm(x), torch.cat([txt_attn_masks, img_attn_masks], dim=1)
 
-    def forward(self, img, txt, img_attn_masks, txt_attn_masks, bool_masked_pos=None, fusion_layer=None,
+    def forward(self, img=None, txt=None, img_attn_masks=None, txt_attn_masks=None, fusion_layer=None,
                 img_token_type_idx=1):
-        x, _ = self.forward_features(img, txt, img_attn_masks, txt_attn_masks, bool_masked_pos, fusion_layer,
-                                     img_token_type_idx)
+        """Reference vlmo.py:415-434 (same positional order)."""
+        x, _ = self.forward_features(img=img, txt=txt, img_attn_masks=img_attn_masks, txt_attn_masks=txt_attn_masks,
+                                     fusion_layer=fusion_layer, img_token_type_idx=img_token_type_idx)
         return self.head(x[:, 0])

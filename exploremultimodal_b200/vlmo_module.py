@@ -130,7 +130,15 @@ class VlmoModule(nn.Module):
         state_dict = self.interpolate_pos_embedding(state_dict)
         is_beit = not any(('.mlp.v' in k or '.mlp.l' in k or '.mlp.vl' in k) for k in state_dict)
         matching = (self._load_beit if is_beit else self._load_vlmo)(state_dict)
+        self.invalidate_weight_cache()
         return matching, is_beit
+
+    def invalidate_weight_cache(self):
+        """See VLMO.invalidate_weight_cache: call after writing parameters through `.data`."""
+        self.transformer.invalidate_weight_cache()
+
+    def attach_to_optimizer(self, optimizer):
+        return self.transformer.attach_to_optimizer(optimizer)
 
     # ---- reference vlmo_module.py:321-393
     def infer(self, batch, infer_mode='img-txt', mask_txt=False, mask_img=False, image_token_type_idx=1,

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MOME_ABI_VERSION 5
+#define MOME_ABI_VERSION 6
 #define MOME_MAX_GROUPS 4
 
 enum MomeStatus { MOME_OK = 0, MOME_ERR_ARG = 1, MOME_ERR_CUDA = 2, MOME_ERR_UNSUPPORTED = 3 };
@@ -239,7 +239,7 @@ typedef struct {
   /* backward only */
   const float* dx2;          /* gradient of the block output */
   float* dx;                 /* gradient of the block input */
-  float *dgamma_1, *dgamma_2, *dn1w, *dn1b, *dn2w, *dn2b, *dqkv_bias /* [3d] */, *dproj_b, *dw_qkv, *dw_proj;
+  float *dgamma_1, *dgamma_2, *dn1w, *dn1b, *dn2w, *dn2b, *dq_bias /* [d] or NULL */, *dv_bias /* [d] or NULL */, *dproj_b, *dw_qkv, *dw_proj;
   void *s_dbr2, *s_dh2, *s_dbr1, *s_do, *s_dh;  /* scratch [tokens, d] (compute dtype) */
   void* s_dz;                /* scratch [tokens, hid] */
   void* s_dqkv;              /* scratch [tokens, 3d] */

@@ -36,14 +36,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.mome_launch_count() == 0
 
 
-def test_struct_layout_matches_header():
-    # MomeGemmGroup: 11 x 8 bytes; MomeGemmArgs: 8 x int32 + 7 x int64 + pointer + 4 groups
-    assert ctypes.sizeof(_lib.GemmGroup) == 88
-    assert ctypes.sizeof(_lib.GemmArgs) == 32 + 56 + 8 + 4 * 88 + 24
-    # MomeBlockGroup: 11 x 8; MomeBlockArgs: 6 x int32 + 3 x int64 + 2 x float + 12 pointers + 4 groups + 38 pointers + size_t
-    assert ctypes.sizeof(_lib.BlockGroup) == 88
-    assert ctypes.sizeof(_lib.BlockArgs) == 24 + 24 + 8 + 12 * 8 + 4 * 88 + 38 * 8 + 8 + 4 * 8 + 24
-    assert ctypes.sizeof(_lib.Dropout) == 32
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof of every ABI struct as the C compiler sees include/mome.h == the ctypes mirror in _lib.py."""
+    import subprocess
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include "mome.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(MomeGemmGroup), sizeof(MomeGemmArgs), sizeof(MomeBlockGroup), sizeof(MomeBlockArgs), '
+                   'sizeof(MomeDropout));return 0;}\n')
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    mine = [ctypes.sizeof(t) for t in (_lib.GemmGroup, _lib.GemmArgs, _lib.BlockGroup, _lib.BlockArgs, _lib.Dropout)]
+    assert mine == sizes, (mine, sizes)
 
 
 def test_state_dict_layout_matches_reference():
