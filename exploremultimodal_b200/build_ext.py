@@ -25,15 +25,29 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _deps_mtime():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))]
+HASH = LIB + '.srchash'
+
+
+def _sources_hash():
+    """sha256 over every csrc/*.cu, csrc/*.cuh, include/mome.h and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(' '.join(FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh')))
     files.append(os.path.join(os.path.dirname(HERE), 'include', 'mome.h'))
-    files.append(os.path.abspath(__file__))
-    return max(os.path.getmtime(f) for f in files)
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def needs_build():
-    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
+    """True unless libmome.so exists and was built from exactly the present sources (content hash, not mtimes:
+    the library travels to the GPU box inside a snapshot whose file times mean nothing)."""
+    if not os.path.exists(LIB) or not os.path.exists(HASH):
+        return True
+    with open(HASH) as f:
+        return f.read().strip() != _sources_hash()
 
 
 def _compile(src):
@@ -58,6 +72,8 @@ def build(force=False, verbose=True):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    with open(HASH, 'w') as f:
+        f.write(_sources_hash() + '\n')
     if verbose:
         print(f'built {LIB} from {len(srcs)} sources')
     return LIB

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -103,29 +104,40 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // bf16x2 <-> fp32 helpers of the epilogue
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
-// GELU and its derivative for two elements at once in packed fp16 (HFMA2 + two MUFU.f16x2 ops): the
-// epilogue of the K = 768 fc1 GEMM has ~0.2 cycles per element per SM before it, not the MMAs, bounds the
-// kernel, and the fp32 erf form costs ~25 issue slots per element. Phi(z) is evaluated in its tanh form,
-// 0.5 (1 + tanh(sqrt(2/pi) (z + 0.044715 z^3))), |error| < 5e-4 against the erf form, i.e. below the
-// resolution of the bf16 values it produces (the fp32 validation path uses exact erff); gelu'(z) =
-// Phi(z) + z phi(z) with phi from ex2.approx.
+// GELU (erf form, reference vlmo.py:114 nn.GELU) and its derivative for two elements at once in packed fp16: the
+// epilogue of the K = 768 fc1 GEMM has ~0.2 cycles per element per SM before it, not the MMAs, bounds the kernel,
+// and fp32 erff costs ~25 issue slots per element. Phi(z) = 0.5 (1 + erf(z / sqrt 2)) is evaluated through the
+// odd approximant
+//     Phi(z) ~= 0.5 (1 + tanh(z (a + b z^2 + c z^4))),   a = 0.797627599, b = 0.0369255429, c = -3.41174313e-4
+// (minimax fit of gelu over [-8, 8]: |gelu - gelu_erf| < 3.1e-5, |gelu' - gelu_erf'| < 1.2e-4 in exact arithmetic,
+// 15x tighter than the usual two-term "tanh GELU" and below half an ulp of the bf16 results for |value| > 0.016);
+// z^2 is clamped at 64, beyond which tanh saturates. One MUFU (tanh.approx.f16x2) per pair: the derivative is the
+// approximant's own, gelu'(z) = Phi + 0.5 z (1 - t^2) (a + 3 b z^2 + 5 c z^4), so forward and backward are consistent.
+// fp16 arithmetic (11-bit significand) adds ~5e-4 relative, the fp32 validation path uses exact erff.
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 template <bool DROP>
 __device__ __forceinline__ void gelu_fast2(float z0, float z1, float m0, float m1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
   const __half2 z = __floats2half2_rn(z0, z1);
-  const __half2 z2 = __hmul2(z, z);
-  const __half2 inner = __hmul2(z, __hfma2(z2, __float2half2_rn(0.0356774081f), __float2half2_rn(0.7978845608f)));
-  uint32_t th, ex;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2_as_u32(inner)));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(ex) : "r"(h2_as_u32(__hmul2(z2, __float2half2_rn(-0.7213475204f)))));  // exp(-z^2/2)
-  const __half2 cdf = __hfma2(u32_as_h2(th), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
-  const __half2 g = __hmul2(z, cdf);
-  const __half2 dg = __hfma2(__hmul2(z, u32_as_h2(ex)), __float2half2_rn(0.3989422804f), cdf);
-  float2 gf = __half22float2(g), dgf = __half22float2(dg);
+  const __half2 z2 = __hmin2(__hmul2(z, z), __float2half2_rn(64.f));
+  const __half2 q = __hfma2(__hfma2(z2, __float2half2_rn(-3.41174313e-4f), __float2half2_rn(0.0369255429f)), z2,
+                            __float2half2_rn(0.797627599f));
+  uint32_t th;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2_as_u32(__hmul2(z, q))));
+  const __half2 t = u32_as_h2(th);
+  const __half2 cdf = __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+  // 0.5 * d/dz [z (a + b z^2 + c z^4)] = 0.5 a + 1.5 b z^2 + 2.5 c z^4
+  const __half2 hdu = __hfma2(__hfma2(z2, __float2half2_rn(2.5f * -3.41174313e-4f), __float2half2_rn(1.5f * 0.0369255429f)), z2,
+                              __float2half2_rn(0.5f * 0.797627599f));
+  const __half2 sech2 = __hfma2(__hneg2(t), t, __float2half2_rn(1.f));
+  __half2 g = __hmul2(z, cdf);
+  __half2 dg = __hfma2(__hmul2(z, hdu), sech2, cdf);
   if (DROP) {  // dropout after the activation (timm Mlp): both the value and the derivative carry mask * scale
-    gf.x *= m0; gf.y *= m1; dgf.x *= m0; dgf.y *= m1;
+    const __half2 m = __floats2half2_rn(m0, m1);
+    g = __hmul2(g, m);
+    dg = __hmul2(dg, m);
   }
+  const float2 gf = __half22float2(g), dgf = __half22float2(dg);
   g_bf16x2 = pack_bf16(gf.x, gf.y);
   dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
 }
@@ -296,150 +308,157 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
       const uint32_t didx0 = drop_group(g.row0 + rfirst, p.N, col_base);
       const float* rs_p = (EPI == MOME_EPI_RESIDUAL && p.row_scale != nullptr) ? p.row_scale + g.row0 + rfirst : nullptr;
 
-      // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
-      // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
-      // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use.
-      constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < 2 ? kChunks : 2) : 1;
-      constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
-      uint2 aux[kAuxDepth][8];
-      float4 res[kResDepth][8];
-      if (EPI == MOME_EPI_DGELU) {
-        const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
-        const long long astep = 4 * p.ldaux * 2;
-#pragma unroll
-        for (int c = 0; c < kAuxDepth; ++c) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (it < nvalid && c < nchunks) aux[c][it] = *reinterpret_cast<const uint2*>(ap + it * astep + c * 64);
+      // The whole per-item epilogue is instantiated twice: FULL = every row / column this warp touches lies inside
+      // the group (all tiles but the last row tile of a group), with no per-iteration bounds predicates, and the
+      // general version for ragged edges.
+      auto epilogue_item = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
+        // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
+        // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use.
+        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < 2 ? kChunks : 2) : 1;
+        constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
+        uint2 aux[kAuxDepth][8];
+        float4 res[kResDepth][8];
+        if (EPI == MOME_EPI_DGELU && !(p.debug & 16)) {
+          const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
+          const long long astep = 4 * p.ldaux * 2;
+  #pragma unroll
+          for (int c = 0; c < kAuxDepth; ++c) {
+  #pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (FULL || (it < nvalid && c < nchunks)) aux[c][it] = *reinterpret_cast<const uint2*>(ap + it * astep + c * 64);
+          }
         }
-      }
-      const char* res_p = static_cast<const char*>(static_cast<const void*>(g.res)) + (rfirst * p.ldres + col_base) * 4;
-      const long long res_step = 4 * p.ldres * 4;
-      if (EPI == MOME_EPI_RESIDUAL) {
-#pragma unroll
-        for (int c = 0; c < kResDepth && c < kChunks; ++c) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (it < nvalid && c < nchunks) res[c][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + c * 128);
+        const char* res_p = static_cast<const char*>(static_cast<const void*>(g.res)) + (rfirst * p.ldres + col_base) * 4;
+        const long long res_step = 4 * p.ldres * 4;
+        if (EPI == MOME_EPI_RESIDUAL) {
+  #pragma unroll
+          for (int c = 0; c < kResDepth && c < kChunks; ++c) {
+  #pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (FULL || (it < nvalid && c < nchunks)) res[c][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + c * 128);
+          }
         }
-      }
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tacc + c * 32, r);
-        tmem_ld_wait();
-        if (c == kChunks - 1) {
-          // all of this warp's accumulator reads are done: hand the TMEM stage back to the MMA issuer
-          tcgen05_fence_before();
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+  #pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tacc + c * 32, r);
+          tmem_ld_wait();
+          if (c == kChunks - 1) {
+            // all of this warp's accumulator reads are done: hand the TMEM stage back to the MMA issuer
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+          }
+          if (p.debug & 2) continue;  // measurement knob: TMEM drain only
+          float* mine = stage_w + lane * kStagePitch;
+  #pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
           __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-        }
-        if (p.debug & 2) continue;  // measurement knob: TMEM drain only
-        float* mine = stage_w + lane * kStagePitch;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-        __syncwarp();
-        if ((p.debug & 1) || c >= nchunks) { __syncwarp(); continue; }  // knob: no epilogue math / global IO
-        const int col = col_base + c * 32;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (EPI != MOME_EPI_ATOMIC && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-        if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* lds_p = stage_w + rsub * kStagePitch + c4;
-        char* op = out_p + c * 32 * osize;
-        char* o2p = out2_p + c * 64;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (it < nvalid) {
-            float4 v = *reinterpret_cast<const float4*>(lds_p + it * 4 * kStagePitch);
-            if (EPI == MOME_EPI_ATOMIC) {
-              atomicAdd(reinterpret_cast<float4*>(op), v);
-            } else {
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              if (EPI == MOME_EPI_GELU) {
-                // z is rounded to bf16 first (what an autocast Linear hands to GELU); out = gelu(z), out2 = gelu'(z)
-                const uint32_t z01 = pack_bf16(v.x, v.y), z23 = pack_bf16(v.z, v.w);
-                const float2 za = unpack_bf16x2(z01), zb = unpack_bf16x2(z23);
-                uint2 u, du;
-                float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (DROP) dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
-                gelu_fast2<DROP>(za.x, za.y, dm.x, dm.y, u.x, du.x);
-                gelu_fast2<DROP>(zb.x, zb.y, dm.z, dm.w, u.y, du.y);
-                *reinterpret_cast<uint2*>(op) = u;
-                *reinterpret_cast<uint2*>(o2p) = du;
-              } else if (EPI == MOME_EPI_RESIDUAL) {
-                // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
-                uint2 bb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                if (DROP) {  // proj_drop / Mlp output dropout acts on the bf16 Linear output
-                  const float4 dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
-                  const float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y);
-                  bb = make_uint2(pack_bf16(t0.x * dm.x, t0.y * dm.y), pack_bf16(t1.x * dm.z, t1.y * dm.w));
-                }
-                if (has_out2) *reinterpret_cast<uint2*>(o2p) = bb;
-                float2 ba = unpack_bf16x2(bb.x), bc = unpack_bf16x2(bb.y);
-                if (rs_p != nullptr) {  // stochastic depth: the whole branch of a dropped sample vanishes
-                  const float rsc = __ldg(rs_p + it * 4);
-                  ba.x *= rsc; ba.y *= rsc; bc.x *= rsc; bc.y *= rsc;
-                }
-                float4 rr = res[c % kResDepth][it];
-                rr.x = fmaf(gm4.x, ba.x, rr.x); rr.y = fmaf(gm4.y, ba.y, rr.y);
-                rr.z = fmaf(gm4.z, bc.x, rr.z); rr.w = fmaf(gm4.w, bc.y, rr.w);
-                *reinterpret_cast<float4*>(op) = rr;
+          if ((p.debug & 1) || (!FULL && c >= nchunks)) { __syncwarp(); continue; }  // knob: no epilogue math / global IO
+          const int col = col_base + c * 32;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (EPI != MOME_EPI_ATOMIC && EPI != MOME_EPI_DGELU && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+          if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* lds_p = stage_w + rsub * kStagePitch + c4;
+          char* op = out_p + c * 32 * osize;
+          char* o2p = out2_p + c * 64;
+  #pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (FULL || it < nvalid) {
+              float4 v = *reinterpret_cast<const float4*>(lds_p + it * 4 * kStagePitch);
+              if (EPI == MOME_EPI_ATOMIC) {
+                atomicAdd(reinterpret_cast<float4*>(op), v);
               } else {
-                if (EPI == MOME_EPI_DGELU) {
-                  const float2 a0 = unpack_bf16x2(aux[c % kAuxDepth][it].x), a1 = unpack_bf16x2(aux[c % kAuxDepth][it].y);
-                  v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
-                }
-                if (osize == 2) {
-                  const uint2 ob = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                  *reinterpret_cast<uint2*>(op) = ob;
-                  if (do_cs) {
-                    const float2 oa = unpack_bf16x2(ob.x), oc = unpack_bf16x2(ob.y);
-                    cs.x += oa.x; cs.y += oa.y; cs.z += oc.x; cs.w += oc.y;
+                if (EPI != MOME_EPI_DGELU) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                if (EPI == MOME_EPI_GELU) {
+                  // out = gelu(z), out2 = gelu'(z), both from the fp32 accumulator + bias rounded once to fp16 (the
+                  // reference's autocast rounds z to bf16 first; fp16 keeps 3 more bits of it)
+                  uint2 u, du;
+                  float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (DROP) dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
+                  gelu_fast2<DROP>(v.x, v.y, dm.x, dm.y, u.x, du.x);
+                  gelu_fast2<DROP>(v.z, v.w, dm.z, dm.w, u.y, du.y);
+                  if (!(p.debug & 8)) *reinterpret_cast<uint2*>(op) = u;
+                  if (!(p.debug & 8)) *reinterpret_cast<uint2*>(o2p) = du;
+                } else if (EPI == MOME_EPI_RESIDUAL) {
+                  // b = bf16(acc + bias) is what the reference's autocast Linear returns; the residual stream stays fp32
+                  uint2 bb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                  if (DROP) {  // proj_drop / Mlp output dropout acts on the bf16 Linear output
+                    const float4 dm = drop_mul4(didx0 + c * 8 + it * p.N, dkey, p.drop_thr, dscale);
+                    const float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y);
+                    bb = make_uint2(pack_bf16(t0.x * dm.x, t0.y * dm.y), pack_bf16(t1.x * dm.z, t1.y * dm.w));
                   }
+                  if (has_out2) *reinterpret_cast<uint2*>(o2p) = bb;
+                  float2 ba = unpack_bf16x2(bb.x), bc = unpack_bf16x2(bb.y);
+                  if (rs_p != nullptr) {  // stochastic depth: the whole branch of a dropped sample vanishes
+                    const float rsc = __ldg(rs_p + it * 4);
+                    ba.x *= rsc; ba.y *= rsc; bc.x *= rsc; bc.y *= rsc;
+                  }
+                  float4 rr = res[c % kResDepth][it];
+                  rr.x = fmaf(gm4.x, ba.x, rr.x); rr.y = fmaf(gm4.y, ba.y, rr.y);
+                  rr.z = fmaf(gm4.z, bc.x, rr.z); rr.w = fmaf(gm4.w, bc.y, rr.w);
+                  *reinterpret_cast<float4*>(op) = rr;
                 } else {
-                  *reinterpret_cast<float4*>(op) = v;
-                  if (do_cs) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
+                  if (EPI == MOME_EPI_DGELU) {
+                    const float2 a0 = unpack_bf16x2(aux[c % kAuxDepth][it].x), a1 = unpack_bf16x2(aux[c % kAuxDepth][it].y);
+                    v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
+                  }
+                  if (osize == 2) {
+                    const uint2 ob = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                    if (!(p.debug & 8)) *reinterpret_cast<uint2*>(op) = ob;
+                    if (do_cs) {
+                      const float2 oa = unpack_bf16x2(ob.x), oc = unpack_bf16x2(ob.y);
+                      cs.x += oa.x; cs.y += oa.y; cs.z += oc.x; cs.w += oc.y;
+                    }
+                  } else {
+                    *reinterpret_cast<float4*>(op) = v;
+                    if (do_cs) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
+                  }
                 }
               }
             }
+            op += out_step;
+            o2p += out2_step;
           }
-          op += out_step;
-          o2p += out2_step;
-        }
-        if (EPI == MOME_EPI_DGELU && c + kAuxDepth < kChunks) {
-          const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
-          const long long astep = 4 * p.ldaux * 2;
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (it < nvalid && c + kAuxDepth < nchunks)
-              aux[c % kAuxDepth][it] = *reinterpret_cast<const uint2*>(ap + it * astep + (c + kAuxDepth) * 64);
-        }
-        if (EPI == MOME_EPI_RESIDUAL && c + kResDepth < kChunks) {
-          // the slot just consumed is refilled with the residual of chunk c + 2
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (it < nvalid && c + kResDepth < nchunks)
-              res[c % kResDepth][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + (c + kResDepth) * 128);
-        }
-        if (do_cs) {
-          // fused bias gradient, stage 1: the stored values summed over this warp's 32 rows go to row
-          // (row0 / 32) of the partials buffer (no atomics; mome_colreduce adds the parts)
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+          if (EPI == MOME_EPI_DGELU && c + kAuxDepth < kChunks && !(p.debug & 16)) {
+            const char* ap = static_cast<const char*>(g.aux) + (rfirst * p.ldaux + col_base) * 2;
+            const long long astep = 4 * p.ldaux * 2;
+  #pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (FULL || (it < nvalid && c + kAuxDepth < nchunks))
+                aux[c % kAuxDepth][it] = *reinterpret_cast<const uint2*>(ap + it * astep + (c + kAuxDepth) * 64);
           }
-          if (rsub == 0 && row0 < g.M) *reinterpret_cast<float4*>(g.colsum + (row0 >> 5) * p.N + col) = cs;
+          if (EPI == MOME_EPI_RESIDUAL && c + kResDepth < kChunks) {
+            // the slot just consumed is refilled with the residual of chunk c + 2
+  #pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (FULL || (it < nvalid && c + kResDepth < nchunks))
+                res[c % kResDepth][it] = *reinterpret_cast<const float4*>(res_p + it * res_step + (c + kResDepth) * 128);
+          }
+          if (do_cs) {
+            // fused bias gradient, stage 1: the stored values summed over this warp's 32 rows go to row
+            // (row0 / 32) of the partials buffer (no atomics; mome_colreduce adds the parts)
+  #pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (rsub == 0 && (FULL || row0 < g.M)) *reinterpret_cast<float4*>(g.colsum + (row0 >> 5) * p.N + col) = cs;
+          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
+      };
+      if (row0 + 32 <= static_cast<long long>(g.M) && nchunks == kChunks) epilogue_item(std::true_type{});
+      else epilogue_item(std::false_type{});
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

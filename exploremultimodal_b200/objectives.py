@@ -63,13 +63,22 @@ class _PeerGather:
     features with plain loads over NVLink — no all_gather, no cat / roll (reference
     objectives.py:401-414, 102-105). Writes and reads are separated by device-side barriers on the
     signal pads (no host synchronisation, capturable in a CUDA graph).
-    Set MOME_ITC_GATHER=nccl to use NCCL all_gather instead."""
+
+    MOME_ITC_GATHER selects the path: `peer` (default: the in-kernel gather; setting it up must succeed,
+    a failure raises), `nccl` (NCCL all_gather + the same kernels on the gathered arrays), `auto` (peer if
+    the symmetric-memory rendezvous works on this system, else NCCL with a warning). `itc_gather_path()`
+    reports which one ran."""
     _cache = {}
+    path = None      # 'peer' | 'nccl' | 'nccl (peer unavailable: ...)' once a multi-rank ITC call has run
 
     @classmethod
     def get(cls, bs, dim, device):
         import os
-        if os.environ.get('MOME_ITC_GATHER', 'peer') != 'peer':
+        mode = os.environ.get('MOME_ITC_GATHER', 'peer')
+        if mode not in ('peer', 'nccl', 'auto'):
+            raise ValueError(f'MOME_ITC_GATHER={mode!r}: expected peer, nccl or auto')
+        if mode == 'nccl':
+            cls.path = 'nccl'
             return None
         key = (bs, dim, str(device))
         if key not in cls._cache:
@@ -78,11 +87,22 @@ class _PeerGather:
                 buf = symm.empty(2, bs, dim, dtype=torch.float32, device=device)
                 hdl = symm.rendezvous(buf, dist.group.WORLD)
                 cls._cache[key] = (buf, hdl)
-            except Exception as e:  # no peer access on this system: NCCL all_gather path (still GPU)
+            except Exception as e:
+                if mode == 'peer':
+                    raise RuntimeError(f'in-kernel ITC gather: symmetric-memory setup failed ({e}); set MOME_ITC_GATHER=nccl '
+                                       'to use NCCL all_gather instead') from e
                 import warnings
                 warnings.warn(f'symmetric-memory ITC gather unavailable ({e}); using NCCL all_gather')
                 cls._cache[key] = None
+                cls.path = f'nccl (peer unavailable: {type(e).__name__})'
+        if cls._cache[key] is not None:
+            cls.path = 'peer'
         return cls._cache[key]
+
+
+def itc_gather_path():
+    """Which cross-rank gather the ITC calls of this process used: 'peer', 'nccl', ... or None (single rank)."""
+    return _PeerGather.path
 
 
 class _ItcFn(torch.autograd.Function):

@@ -1,7 +1,8 @@
 """Generate tests/golden/*.pt from the UNMODIFIED reference (run in the build container only).
 
-    python oracle/gen_golden.py            # writes tests/golden/{unit_full,unit_ragged,unit_vqa}.pt
+    python oracle/gen_golden.py            # writes tests/golden/{unit_full,unit_ragged,unit_vqa,base_c1}.pt
                                            #        tests/golden/state_dict_shapes.json
+    python oracle/gen_golden.py base_c1    # only the named case(s)
 
 The reference's models/vlmo/{vlmo,vlmo_module,objectives,heads}.py are imported from
 /root/reference through the timm shim in oracle/ref_shim; nothing is copied.
@@ -39,7 +40,7 @@ def summarize(name, t):
     return dict(norm=float(t.norm()), sum=float(t.sum()), probe=t[idx].float().clone(), numel=t.numel())
 
 
-def run_reference(cfg, batch):
+def run_reference(cfg, batch, summaries_only=False):
     from models.build import build_model  # reference models/build.py:4
     torch.manual_seed(0)
     model = build_model(cfg)
@@ -61,9 +62,11 @@ def run_reference(cfg, batch):
 
     def infer_spy(*a, **k):
         r = orig_infer(*a, **k)
+        n = len(infer_feats)
+        keep = (lambda name, t: summarize(name, t)) if summaries_only else (lambda name, t: t.detach().clone())
         infer_feats.append(dict(mode=k.get('infer_mode', a[1] if len(a) > 1 else 'img-txt'),
-                                co_feats=r['co_feats'].detach().clone(),
-                                cls_feats=r['cls_feats'].detach().clone()))
+                                co_feats=keep(f'infer{n}.co_feats', r['co_feats']),
+                                cls_feats=keep(f'infer{n}.cls_feats', r['cls_feats'])))
         return r
     model.infer = infer_spy
 
@@ -89,7 +92,9 @@ def run_reference(cfg, batch):
     )
     for k in ('sim_i2t', 'sim_t2i', 'itm_logits', 'mlm_logits', 'vqa_logits'):
         if k in out:
-            gold[k] = out[k].detach().clone()
+            big = summaries_only and out[k].numel() > 4096
+            gold[k + '_summary' if big else k] = summarize(k, out[k]) if big else out[k].detach().clone()
+    gold['summaries_only'] = summaries_only
     return gold
 
 
@@ -103,16 +108,24 @@ def main():
                          bs=2, lengths='realistic', seed=5, vqa=True),
     }
     cases['unit_vqa']['cfg'].data.vqav2_label_size = 37
+    # BASELINE configs[0]: VLMo-base (12 layers, d 768, 3 experts), batch 2, 224^2 + 40 tokens, fp32 on the CPU.
+    # Summaries only (norm, sum, 8 probes per tensor) so that the fixture stays well under 1 MB.
+    cases['base_c1'] = dict(cfg=make_config('vlmo_base', parity=True), bs=2, lengths='full', seed=2024, summaries_only=True)
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
     for name, c in cases.items():
+        if only and name not in only:
+            continue
         batch = make_batch(c['cfg'], c['bs'], seed=c['seed'], lengths=c['lengths'], vqa=c.get('vqa', False))
-        gold = run_reference(c['cfg'], batch)
-        gold['case'] = dict(model='vlmo_unit', phase=c['cfg'].train.phase, loss_names=list(c['cfg'].train.loss_names),
+        gold = run_reference(c['cfg'], batch, summaries_only=c.get('summaries_only', False))
+        gold['case'] = dict(model=c['cfg'].model.name, phase=c['cfg'].train.phase, loss_names=list(c['cfg'].train.loss_names),
                             bs=c['bs'], lengths=c['lengths'], seed=c['seed'], vqa=c.get('vqa', False),
                             vqav2_label_size=c['cfg'].data.vqav2_label_size)
         torch.save(gold, os.path.join(out_dir, name + '.pt'))
         print(name, 'total_loss', gold['total_loss'], 'block calls', len(gold['route_log']),
               'params with grad', len(gold['grads']))
 
+    if only:
+        return
     # state_dict key/shape listing of the real configs (pins oracle.state_dict_shapes and the
     # product module's state_dict layout)
     listing = {}

@@ -1,5 +1,6 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the CPU port of the reference's step, the one place besides
-the tests where bench.py executes `oracle/`) prints exactly one JSON line with the keys the measurement contract names.
+"""CPU: the reference arm of bench.py (`--impl reference`: the unmodified reference's step on the host cores when its
+sources are present (/root/reference or the mirror oracle/_ref), else the CPU port; the one place besides the tests where
+bench.py executes `oracle/`) prints exactly one JSON line with the keys the measurement contract names.
 The product arm needs a GPU; its line is checked by the driver."""
 import json
 import os
@@ -23,7 +24,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d['higher_is_better'] is True and d['scaling'] == 'weak' and d['vs_baseline'] is None
     assert d['data'] == 'synthetic' and 'workload' in d['config'] and 'model' not in d['config']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['unit'] == 'samples/s' and cb['value'] == d['value'] and cb['sample']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['unit'] == 'samples/s' and cb['value'] == d['value'] and cb['sample']
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == 'samples/s' and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
 
@@ -38,3 +39,13 @@ def test_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
+
+
+def test_reference_arm_other_workloads():
+    """configs[3] (VQA at 480^2) and configs[4] (ITC only) have their own reference-arm lines."""
+    for wl, metric in (('itc4096', 'vlmo_base_itc_samples_per_sec'),):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', wl, '--steps', '1',
+                            '--warmup', '0', '--cpu-batch', '2'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][0])
+        assert d['metric'] == metric and d['value'] > 0 and d['impl'] == 'reference'

@@ -41,8 +41,9 @@ def _expected_groups(route_log, T):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-@pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa'])
+@pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa', 'base_c1'])
 def test_module_matches_reference_golden(name, precision):
+    """base_c1 = BASELINE configs[0] (VLMo-base 12L, batch 2, 224^2 + 40 tokens) as the unmodified reference computed it."""
     gold = load_golden(name)
     cfg = case_config(gold['case'])
     model = _build(cfg, precision)
@@ -75,6 +76,10 @@ def test_module_matches_reference_golden(name, precision):
         n = gold['mlm_logits'].shape[0]
         assert int(out['mlm_count']) == n
         assert rel_err(out['mlm_logits'][:n].float(), gold['mlm_logits']) < tol
+    if 'mlm_logits_summary' in gold:
+        n = gold['mlm_logits_summary']['numel'] // cfg.model.vocab_size
+        assert int(out['mlm_count']) == n
+        check_summary('mlm_logits', out['mlm_logits'][:n].float(), gold['mlm_logits_summary'], tol, what='logits ')
     for k, v in gold['scalars'].items():
         if 'count' in k and k in out:
             assert int(out[k]) == int(v), k

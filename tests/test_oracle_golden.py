@@ -14,8 +14,9 @@ from oracle import mome_oracle as O
 FP32_TOL = 1e-4
 
 
-@pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa'])
+@pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa', 'base_c1'])
 def test_oracle_matches_reference_golden(name):
+    """base_c1 = BASELINE configs[0]: VLMo-base (12 layers, d 768), batch 2, 224^2 + 40 tokens, fp32 on the CPU."""
     gold = load_golden(name)
     cfg = case_config(gold['case'])
     batch = case_batch(cfg, gold['case'])
@@ -34,6 +35,8 @@ def test_oracle_matches_reference_golden(name):
     for k in ('sim_i2t', 'sim_t2i', 'itm_logits', 'mlm_logits', 'vqa_logits'):
         if k in gold:
             assert rel_err(ret[k], gold[k]) < FP32_TOL, k
+        if k + '_summary' in gold:
+            check_summary(k, ret[k], gold[k + '_summary'], FP32_TOL, what='logits ')
     for k, v in gold['scalars'].items():
         if k in ret and 'count' in k:
             assert int(ret[k]) == int(v), k

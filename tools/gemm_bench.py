@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--tokens', type=int, default=30336)
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--d', type=int, default=768)
+    ap.add_argument('--only', default='', help='comma-separated substrings of the case names to run')
     a = ap.parse_args()
     M, d = a.tokens, a.d
     hid = 4 * d
@@ -63,7 +64,10 @@ def main():
         ('proj  wgrad ATOMIC  ', d, d, lambda: ops.gemm(L.BF16, MN, MN, L.EPI_ATOMIC, L.F32, d, d, d, d, [dict(a=P(x), b=P(x), M=d, K=M, out=P(gw))])),
     ]
     print(f'tokens {M} d {d}  MOME_GEMM_DEBUG={os.environ.get("MOME_GEMM_DEBUG", "0")}')
+    only = [o for o in a.only.split(',') if o]
     for name, n, k, fn in cases + wcases:
+        if only and not any(o in name for o in only):
+            continue
         flops = 2.0 * M * n * k
         for _ in range(3):
             fn()
