@@ -62,6 +62,10 @@ def parse():
                     help="'shipped': drop_rate / attn_drop_rate / drop_path_rate = 0.1 as in the reference's conf/model/vlmo_base.yaml; "
                          "'off': the parity configuration")
     ap.add_argument('--reduce-dtype', default='fp32', choices=['fp32', 'bf16'], help='dtype of the gradient all-reduce (N > 1)')
+    ap.add_argument('--dedup', action='store_true',
+                    help='opt-in cross-pass de-duplication of the pre-fusion layers (config.train.dedup_prefix, SURVEY.md 8(f) N3): '
+                         'NOT the reference pass structure; its line carries no model-FLOP fraction')
+    ap.add_argument('--no-merge', action='store_true', help='one backbone pass per reference infer() call (config.train.merge_passes = False)')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--ncu-step', action='store_true',
                     help='after warm-up run ONE eager step between cudaProfilerStart/Stop and exit '
@@ -80,6 +84,8 @@ def workload_config(args, world=1):
     cfg = make_config(args.model, phase=phase, loss_names=losses, global_reduce=world > 1,
                       parity=args.dropout == 'off', img_size=img)
     cfg.model.precision = args.precision
+    cfg.train.dedup_prefix = bool(getattr(args, 'dedup', False))
+    cfg.train.merge_passes = not getattr(args, 'no_merge', False)
     return cfg
 
 
@@ -539,6 +545,10 @@ def run_mome(args):
               'dropout': {'drop_rate': cfg.model.drop_rate, 'attn_drop_rate': cfg.model.attn_drop_rate,
                           'drop_path_rate': cfg.model.drop_path_rate}, 'cuda_graph': bool(had_graph), 'attention': attention,
               'l2': 'per-step working set (tens of GB of activations) far exceeds the 126 MB L2; no flush needed'}
+    config['passes'] = ('merged: ITC = 1 packed two-modality pass, MLM + ITM = 1 pass over 4 B sequences' if cfg.train.merge_passes and not args.dedup
+                        else 'one pass per reference infer() call')
+    if args.dedup:
+        config['dedup_prefix'] = 'pre-fusion layers computed once per image / caption per step (opt-in; not the reference pass structure)'
     if world > 1:
         config['itc_gather'] = objectives.itc_gather_path()
         config['itc_parity'] = checks.get('itc_parity')
@@ -549,9 +559,10 @@ def run_mome(args):
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': args.precision, 'data': 'synthetic', 'config': config,
         'samples_per_sec_per_gpu': value / world,
-        'model_tflops_per_gpu': fps * B / (ms_step * 1e-3) / 1e12,
-        'model_flops_frac_of_sustained_peak': fps * B / (ms_step * 1e-3) / 1e12 / sustained,
-        'model_flops_frac_of_burst_peak': fps * B / (ms_step * 1e-3) / 1e12 / burst,
+        # algorithmic FLOPs of the REFERENCE pass structure: meaningless for the de-duplicated run, which does less work
+        'model_tflops_per_gpu': None if args.dedup else fps * B / (ms_step * 1e-3) / 1e12,
+        'model_flops_frac_of_sustained_peak': None if args.dedup else fps * B / (ms_step * 1e-3) / 1e12 / sustained,
+        'model_flops_frac_of_burst_peak': None if args.dedup else fps * B / (ms_step * 1e-3) / 1e12 / burst,
         'eager_ms_per_step': eager_ms_step,
         'loss': final_loss,
         'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,

@@ -327,8 +327,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     const uint32_t dkey = DROP ? drop_mix(p.drop_salt, __ldg(p.drop_seed)) : 0u;
     const float dscale = drop_scale(p.drop_thr);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint8_t* prow = smem + kPOff + half * 16384 + row * 128;  // this thread's 128-byte segment of the P tile (64 keys)
-    uint8_t* srow = smem + kSOff + half * 16384 + row * 128;
+    // this thread's 128-byte segment of the P / dS tiles (64 keys), as shared-space addresses (st.shared, not generic st)
+    const uint32_t prow = smem_u32(smem + kPOff + half * 16384 + row * 128);
+    const uint32_t srow = smem_u32(smem + kSOff + half * 16384 + row * 128);
     const int sw = row & 7;
     const long long ld3 = 3LL * d;
     uint32_t blk = 0, jcount = 0;
@@ -390,10 +391,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
             }
             if (EARLY_S && c == 0 && blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // first store of the block
             // keys c 16 + [0, 16) of this thread's 64: 16-byte chunks 2 c and 2 c + 1 of the row segment
-            *reinterpret_cast<uint4*>(prow + (((2 * c) ^ sw) << 4)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-            *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
-            *reinterpret_cast<uint4*>(srow + (((2 * c) ^ sw) << 4)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
-            *reinterpret_cast<uint4*>(srow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(ds[4], ds[5], ds[6], ds[7]);
+            sts_v4_u32(prow + (((2 * c) ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
+            sts_v4_u32(prow + (((2 * c + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
+            sts_v4_u32(srow + (((2 * c) ^ sw) << 4), ds[0], ds[1], ds[2], ds[3]);
+            sts_v4_u32(srow + (((2 * c + 1) ^ sw) << 4), ds[4], ds[5], ds[6], ds[7]);
           }
           fence_proxy_async();  // the tiles are read by the tensor core (async proxy)
           tcgen05_fence_before();

@@ -279,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
     const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int half = ew >> 2;              // which half of the tile's columns
-    float* stage_w = epi_stage + ew * (kStageBytesPerWarp / 4);
+    const uint32_t stage_u32 = smem_u32(epi_stage + ew * (kStageBytesPerWarp / 4));  // this warp's transpose tile
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -315,8 +315,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
         // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
-        // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use.
-        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < 2 ? kChunks : 2) : 1;
+        // lane-iteration): the first chunks up front (three for gelu', two for the residual), then that many chunks ahead
+        // of their use (ncu: with two, the gelu' loads of chunks 2 and 3 still stalled their first use on the long scoreboard).
+        constexpr int kAuxWant = DROP ? 3 : 2;  // DGELU has no dropout of its own: the flag selects the prefetch depth (measurement)
+        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < kAuxWant ? kChunks : kAuxWant) : 1;
         constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
         uint2 aux[kAuxDepth][8];
         float4 res[kResDepth][8];
@@ -356,11 +358,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
           }
           if (p.debug & 2) continue;  // measurement knob: TMEM drain only
-          float* mine = stage_w + lane * kStagePitch;
+          const uint32_t mine = stage_u32 + lane * (kStagePitch * 4);
   #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(mine + 4 * i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            sts_v4_u32(mine + 16 * i, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           __syncwarp();
           if ((p.debug & 1) || (!FULL && c >= nchunks)) { __syncwarp(); continue; }  // knob: no epilogue math / global IO
           const int col = col_base + c * 32;
@@ -368,13 +369,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
           if (EPI != MOME_EPI_ATOMIC && EPI != MOME_EPI_DGELU && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
           if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* lds_p = stage_w + rsub * kStagePitch + c4;
+          const uint32_t lds_a = stage_u32 + (rsub * kStagePitch + c4) * 4;
           char* op = out_p + c * 32 * osize;
           char* o2p = out2_p + c * 64;
   #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (FULL || it < nvalid) {
-              float4 v = *reinterpret_cast<const float4*>(lds_p + it * 4 * kStagePitch);
+              float4 v = lds_v4(lds_a + it * (16 * kStagePitch));
               if (EPI == MOME_EPI_ATOMIC) {
                 atomicAdd(reinterpret_cast<float4*>(op), v);
               } else {
@@ -554,7 +555,9 @@ int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_
   } else if (!a_mn && b_mn) {
     switch (p.epilogue) {
       case MOME_EPI_STORE: return launch_one<BLOCK_N, false, true, MOME_EPI_STORE>(p, grid, stream);
-      case MOME_EPI_DGELU: return launch_one<BLOCK_N, false, true, MOME_EPI_DGELU>(p, grid, stream);
+      case MOME_EPI_DGELU:
+        return (p.debug & 32) ? launch_one<BLOCK_N, false, true, MOME_EPI_DGELU, false>(p, grid, stream)
+                              : launch_one<BLOCK_N, false, true, MOME_EPI_DGELU, true>(p, grid, stream);
       case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, false, true, MOME_EPI_ATOMIC>(p, grid, stream);
     }
   } else if (a_mn && b_mn) {

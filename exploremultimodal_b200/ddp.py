@@ -28,7 +28,8 @@ class GradSync:
         assert reduce_dtype in ('fp32', 'bf16')
         self.world = world
         self.reduce_dtype = reduce_dtype
-        self.comm = torch.cuda.Stream() if world > 1 else None
+        cuda = next(model.parameters()).is_cuda
+        self.comm = torch.cuda.Stream() if (world > 1 and cuda) else None  # CPU (gloo, tests): reduce inline
         in_block = set()
         self.blocks = []
         self.block_flat = []
@@ -80,6 +81,9 @@ class GradSync:
         if blk._flat_grad is None:
             return
         self._fired.add(id(blk))
+        if self.comm is None:
+            self._all_reduce(blk._flat_grad)
+            return
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
             self._all_reduce(blk._flat_grad)
@@ -107,7 +111,7 @@ class GradSync:
             late = blk._pending_bwd != 0 or id(blk) not in self._fired or moved
             blk._pending_bwd = 0
             if self.world > 1 and late and blk._flat_grad is not None:
-                if id(blk) in self._fired:      # a stale buffer went out earlier: wait for it before reducing again
+                if id(blk) in self._fired and self.comm is not None:  # a stale buffer went out earlier: wait for it first
                     torch.cuda.current_stream().wait_stream(self.comm)
                 self._all_reduce(blk._flat_grad)
         self._fired.clear()
@@ -117,4 +121,5 @@ class GradSync:
             return
         if self.rest_flat is not None:
             self._all_reduce(self.rest_flat)
-        torch.cuda.current_stream().wait_stream(self.comm)
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)

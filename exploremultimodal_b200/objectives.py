@@ -23,29 +23,50 @@ def compute_accuracy(logits, target):
 
 
 # --------------------------------------------------------------------------------------------- MLM
-def compute_mlm(model, batch):
-    """Reference objectives.py:40-78. Masked rows are compacted with a stable sort instead of
-    boolean indexing (no host sync): the first K rows hold every masked position (K = capacity,
-    `config.train.mlm_capacity`, default 25 % of the text tokens, all of them for small batches);
-    the padding rows carry label -100 and are ignored by the cross-entropy exactly like the
-    reference's `ignore_index`."""
-    has_img = any('image' in k for k in batch.keys() if batch[k] is not None)
-    infer = model.infer(batch, infer_mode='img-txt' if has_img else 'txt_only', mask_txt=True, mask_img=False)
-    txt_feats, labels = infer['txt_feats'], infer['txt_labels']
+def compact_masked_rows(labels_flat, capacity):
+    """Indices of the first `capacity` rows whose label is not -100, in order, without a host synchronisation
+    (the reference's boolean indexing `mlm_logits[mlm_labels != -100]` needs the count on the host,
+    objectives.py:52-66). Returns (order [capacity] int64, targets [capacity] with -100 in the unused tail,
+    overflow = number of masked rows that did not fit, a device scalar the caller can log or assert on)."""
+    n = labels_flat.numel()
+    valid = labels_flat != -100
+    pos = torch.cumsum(valid, 0) - 1                               # rank of every masked row among the masked rows
+    n_valid = pos[-1] + 1
+    dest = torch.where(valid & (pos < capacity), pos, torch.full_like(pos, capacity))  # slot `capacity` = discard
+    order = torch.zeros(capacity + 1, dtype=torch.int64, device=labels_flat.device)
+    order.scatter_(0, dest, torch.arange(n, device=labels_flat.device))
+    order = order[:capacity]
+    k = torch.arange(capacity, device=labels_flat.device)
+    targets = torch.where(k < n_valid, labels_flat[order], torch.full_like(k, -100))
+    return order, targets, (n_valid - capacity).clamp(min=0)
+
+
+def mlm_from_feats(model, txt_feats, labels, txt_ids):
+    """MLM head + loss on the text rows of a backbone pass (reference objectives.py:52-78); see compute_mlm."""
     B, T, d = txt_feats.shape
     flat = labels.reshape(-1)
     cap = getattr(model.config.train, 'mlm_capacity', 0.25)
     K = B * T if B * T <= 256 else min(B * T, max(256, int(cap * B * T)))
-    order = torch.argsort((flat == -100).to(torch.int8), stable=True)[:K]
+    order, tgt, overflow = compact_masked_rows(flat, K)
     rows = txt_feats.reshape(B * T, d)[order]
-    tgt = flat[order]
     with model.transformer._autocast():
         logits = model.mlm_head(rows)
     acc, count = compute_accuracy(logits, tgt)
     loss = F.cross_entropy(logits.float().view(-1, model.config.model.vocab_size), tgt.view(-1), ignore_index=-100,
                            reduction='sum') / count.clamp(min=1).float()
-    return {'mlm_task_loss': loss, 'mlm_logits': logits, 'mlm_labels': tgt, 'mlm_ids': infer['txt_ids'],
-            'mlm_mean_acc': acc, 'mlm_count': count}
+    return {'mlm_task_loss': loss, 'mlm_logits': logits, 'mlm_labels': tgt, 'mlm_ids': txt_ids,
+            'mlm_mean_acc': acc, 'mlm_count': count, 'mlm_overflow': overflow}
+
+
+def compute_mlm(model, batch):
+    """Reference objectives.py:40-78. Masked rows are compacted to a fixed capacity instead of boolean indexing
+    (no host sync): the first K rows hold every masked position (K = `config.train.mlm_capacity`, default 25 % of
+    the text tokens — BERT masks 15 % — and all of them for small batches); unused rows carry label -100 and are
+    ignored by the cross-entropy exactly like the reference's `ignore_index`. `mlm_overflow` (device scalar) counts
+    masked tokens beyond the capacity: 0 in every regular batch, and checkable without stalling the step."""
+    has_img = any('image' in k for k in batch.keys() if batch[k] is not None)
+    infer = model.infer(batch, infer_mode='img-txt' if has_img else 'txt_only', mask_txt=True, mask_img=False)
+    return mlm_from_feats(model, infer['txt_feats'], infer['txt_labels'], infer['txt_ids'])
 
 
 # --------------------------------------------------------------------------------------------- ITC
@@ -205,8 +226,13 @@ def compute_itc(model, batch):
     with torch.no_grad():
         model.itc_temp.data.clamp_(0, 4.6052)
     temp = model.itc_temp.exp()
-    img_infer = model.infer(batch, infer_mode='img_only')
-    txt_infer = model.infer(batch, infer_mode='txt_only')
+    if getattr(model.config.train, 'merge_passes', True) and getattr(model, '_prefix', None) is None:
+        # the img_only and txt_only passes as ONE packed pass: text rows -> 'l', image rows -> 'v' in every layer,
+        # separate attention per modality (the same math per token as two reference passes, vlmo.py:369-387)
+        img_infer, txt_infer = model.infer_pair(batch)
+    else:
+        img_infer = model.infer(batch, infer_mode='img_only')
+        txt_infer = model.infer(batch, infer_mode='txt_only')
     with model.transformer._autocast():
         i_feat = model.itc_head(img_infer['co_feats'][:, 0], 'v')
         t_feat = model.itc_head(txt_infer['co_feats'][:, 0], 'l')
@@ -227,37 +253,75 @@ def pick_negatives_argmax(weights):
     return weights.argmax(dim=1)
 
 
-def compute_itm(model, batch, sim_dict=None):
-    """Reference objectives.py:239-314."""
-    txt_ids, txt_mask, img = batch['text_ids'], batch['text_mask'], batch['image']
-    bs = img.size(0)
-    output_pos = model.infer(batch, infer_mode='img-txt')
+def sample_itm_negatives(model, bs, device, sim_dict=None):
+    """Hard-negative indices (reference objectives.py:250-277): one image per text and one text per image, drawn
+    from softmax(sim) with the diagonal removed, on the device."""
     with torch.no_grad():
         if sim_dict is not None:
             w_i2t = F.softmax(sim_dict['sim_i2t'][:, :bs].float(), dim=1) + 1e-5
             w_t2i = F.softmax(sim_dict['sim_t2i'][:, :bs].float(), dim=1) + 1e-5
         else:
-            w_i2t = F.softmax(torch.randn(bs, bs, device=img.device), dim=1) + 1e-5
-            w_t2i = F.softmax(torch.randn(bs, bs, device=img.device), dim=1) + 1e-5
+            w_i2t = F.softmax(torch.randn(bs, bs, device=device), dim=1) + 1e-5
+            w_t2i = F.softmax(torch.randn(bs, bs, device=device), dim=1) + 1e-5
         w_i2t.fill_diagonal_(0)
         w_t2i.fill_diagonal_(0)
         pick = getattr(model, 'itm_negative_picker', pick_negatives_multinomial)
-        neg_img, neg_txt = pick(w_t2i), pick(w_i2t)
+        return pick(w_t2i), pick(w_i2t)   # neg_img, neg_txt
+
+
+def itm_from_cls(model, cls_feat, bs, neg_img, neg_txt):
+    """ITM head + loss on [positives (bs) | negatives (2 bs)] pooled features (reference objectives.py:293-314)."""
+    with model.transformer._autocast():
+        itm_logits = model.itm_head(cls_feat)
+    itm_labels = torch.cat([torch.ones(bs, dtype=torch.long, device=cls_feat.device),
+                            torch.zeros(2 * bs, dtype=torch.long, device=cls_feat.device)], dim=0)
+    itm_loss = F.cross_entropy(itm_logits.float(), itm_labels)
+    acc, count = compute_accuracy(itm_logits, itm_labels)
+    return {'itm_task_loss': itm_loss, 'itm_logits': itm_logits, 'itm_labels': itm_labels, 'itm_mean_acc': acc,
+            'itm_count': count, 'itm_neg_img': neg_img, 'itm_neg_txt': neg_txt}
+
+
+def compute_itm(model, batch, sim_dict=None):
+    """Reference objectives.py:239-314."""
+    txt_ids, txt_mask, img = batch['text_ids'], batch['text_mask'], batch['image']
+    bs = img.size(0)
+    output_pos = model.infer(batch, infer_mode='img-txt')
+    neg_img, neg_txt = sample_itm_negatives(model, bs, img.device, sim_dict)
     neg_batch = {
         'text_ids': torch.cat([txt_ids, txt_ids[neg_txt]], dim=0),
         'text_mask': torch.cat([txt_mask, txt_mask[neg_txt]], dim=0),
         'image': torch.cat([img[neg_img], img], dim=0),
     }
+    if getattr(model, '_prefix', None) is not None:
+        # de-duplicated pre-fusion layers: the negatives are row gathers of the cached per-sample branches
+        ar = torch.arange(bs, device=img.device)
+        neg_batch['_prefix_index'] = (torch.cat([neg_img, ar]), torch.cat([ar, neg_txt]))
     output_neg = model.infer(neg_batch, infer_mode='img-txt')
     cls_feat = torch.cat([output_pos['cls_feats'], output_neg['cls_feats']], dim=0)
-    with model.transformer._autocast():
-        itm_logits = model.itm_head(cls_feat)
-    itm_labels = torch.cat([torch.ones(bs, dtype=torch.long, device=img.device),
-                            torch.zeros(2 * bs, dtype=torch.long, device=img.device)], dim=0)
-    itm_loss = F.cross_entropy(itm_logits.float(), itm_labels)
-    acc, count = compute_accuracy(itm_logits, itm_labels)
-    return {'itm_task_loss': itm_loss, 'itm_logits': itm_logits, 'itm_labels': itm_labels, 'itm_mean_acc': acc,
-            'itm_count': count, 'itm_neg_img': neg_img, 'itm_neg_txt': neg_txt}
+    return itm_from_cls(model, cls_feat, bs, neg_img, neg_txt)
+
+
+def compute_mlm_itm_merged(model, batch, sim_dict=None):
+    """MLM + ITM with their three img-txt backbone passes (MLM: B masked captions; ITM positives: B; ITM negatives:
+    2 B; reference objectives.py:44-47, 247, 291) packed into ONE pass over 4 B independent sequences:
+      rows [0, B)    (image, masked caption)     -> MLM head on the text rows
+      rows [B, 2B)   (image, caption)            -> ITM positives
+      rows [2B, 3B)  (negative image, caption)   -> ITM negatives, same order as the reference's neg_batch
+      rows [3B, 4B)  (image, negative caption)
+    Every sequence goes through exactly the computation the reference gives it (sequences never interact), so losses
+    and gradients are the reference's; what changes is 3 x fewer kernel launches and 4 x larger grouped GEMMs."""
+    txt_ids, txt_mask, img = batch['text_ids'], batch['text_mask'], batch['image']
+    bs = img.size(0)
+    neg_img, neg_txt = sample_itm_negatives(model, bs, img.device, sim_dict)
+    merged = {
+        'text_ids': torch.cat([batch['text_ids_mlm'], txt_ids, txt_ids, txt_ids[neg_txt]], dim=0),
+        'text_mask': torch.cat([txt_mask, txt_mask, txt_mask, txt_mask[neg_txt]], dim=0),
+        'image': torch.cat([img, img, img[neg_img], img], dim=0),
+    }
+    out = model.infer(merged, infer_mode='img-txt')
+    ret = mlm_from_feats(model, out['txt_feats'][:bs], batch['text_labels_mlm'], batch['text_ids_mlm'])
+    ret.update(itm_from_cls(model, out['cls_feats'][bs:], bs, neg_img, neg_txt))
+    return ret
 
 
 # --------------------------------------------------------------------------------------------- VQA

@@ -302,7 +302,8 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     for i, (s, n, route) in enumerate(lay.groups):
         dw1, db1 = buf(('mlp', route, 0), hid, d), buf(('mlp', route, 1), hid)
         dw2, db2 = buf(('mlp', route, 2), d, hid), buf(('mlp', route, 3), d)
-        part = torch.empty((n + 31) // 32, hid, **f32)  # the DGELU epilogue writes every slab of every column once
+        # bf16 path: the DGELU epilogue writes every slab of every column exactly once; fp32 validation path: atomics
+        part = (torch.empty if p.code == L.BF16 else torch.zeros)((n + 31) // 32, hid, **f32)
         grads[('mlp', route)] = (dw1, db1, dw2, db2)
         g = a.group[i]
         g.dw1, g.db1, g.dw2, g.db2, g.colsum_part = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), part.data_ptr()

@@ -488,6 +488,60 @@ class VLMO(nn.Module):
         x = torch.cat([x[:B * T].view(B, T, d), x[B * T:].view(B, P, d)], 1)
         return self._final_norm(x), torch.cat([txt_attn_masks, img_attn_masks], dim=1)
 
+    def forward_features_pair(self, img, txt, img_attn_masks, txt_attn_masks, bool_masked_pos=None, img_token_type_idx=1):
+        """forward_features(img only) and forward_features(txt only) (reference vlmo.py:369-387) as ONE pass over a packed
+        buffer: in every layer the text rows form expert group 'l', the image rows group 'v' (one grouped GEMM), and
+        attention stays within each modality's sequence. Returns (img_feats [B, P, d], txt_feats [B, T, d]), both
+        after the final norm."""
+        depth = len(self.blocks)
+        xi = self.embed_img(img, img_attn_masks, bool_masked_pos, img_token_type_idx)
+        xt = self.embed_txt(txt, txt_attn_masks)
+        B, T, d = xt.shape
+        P = xi.shape[1]
+        x = torch.cat([xt.reshape(B * T, d), xi.reshape(B * P, d)], 0).float()
+        key_mask = torch.cat([txt_attn_masks.reshape(-1), img_attn_masks.reshape(-1)]).to(torch.uint8)
+        split = self._layout('split', B, T, P, x.device)
+        x = self._final_norm(self._run(x, [(i, split) for i in range(depth)], key_mask))
+        return x[B * T:].view(B, P, d), x[:B * T].view(B, T, d)
+
+    # ---- cross-pass de-duplication of the pre-fusion layers (opt-in, SURVEY.md 8(f) N3) ----------------------
+    # Before the fusion layer a sample's image rows and text rows never meet (reference vlmo.py:402-404: two
+    # separate Block calls per layer), so blocks[:F] of the image branch depend on the image alone and those of
+    # the text branch on the text alone. One pretraining step runs them 5 x per image and 4 x per unmasked
+    # caption (MLM, ITC, ITM positives, ITM negatives are permutations of the batch). `encode_prefix` computes
+    # such a branch once; `forward_features_from_prefix` continues from (row-gathered) prefixes. Exact when the
+    # drop rates are 0; with dropout the passes would share their pre-fusion noise, hence opt-in.
+    def encode_prefix(self, route, x, masks, bool_masked_pos=None, img_token_type_idx=1, fusion_layer=None):
+        """route 'v': x = images, 'l': x = token ids. Returns [B, N, d] fp32 after embeddings + blocks[:F]."""
+        assert route in ('v', 'l')
+        Fz = fusion_layer or self.fusion_layer
+        emb = (self.embed_img(x, masks, bool_masked_pos, img_token_type_idx) if route == 'v' else self.embed_txt(x, masks))
+        B, N, d = emb.shape
+        lay = self._layout(route, B, N, N, emb.device)
+        rows = self._run(emb.reshape(B * N, d).float(), [(i, lay) for i in range(Fz)], masks.reshape(-1).to(torch.uint8))
+        return rows.view(B, N, d)
+
+    def forward_features_from_prefix(self, img_pre=None, txt_pre=None, img_attn_masks=None, txt_attn_masks=None,
+                                     fusion_layer=None):
+        """Same results as forward_features, starting from the outputs of encode_prefix."""
+        depth = len(self.blocks)
+        Fz = fusion_layer or self.fusion_layer
+        if txt_pre is None or img_pre is None:
+            route = 'v' if txt_pre is None else 'l'
+            x, masks = (img_pre, img_attn_masks) if txt_pre is None else (txt_pre, txt_attn_masks)
+            B, N, d = x.shape
+            lay = self._layout(route, B, N, N, x.device)
+            y = self._run(x.reshape(B * N, d), [(i, lay) for i in range(Fz, depth)], masks.reshape(-1).to(torch.uint8))
+            return self._final_norm(y.view(B, N, d)), masks
+        B, T, d = txt_pre.shape
+        P = img_pre.shape[1]
+        x = torch.cat([txt_pre.reshape(B * T, d), img_pre.reshape(B * P, d)], 0)
+        key_mask = torch.cat([txt_attn_masks.reshape(-1), img_attn_masks.reshape(-1)]).to(torch.uint8)
+        fused = self._layout('fused', B, T, P, x.device)
+        x = self._run(x, [(i, fused) for i in range(Fz, depth)], key_mask)
+        x = torch.cat([x[:B * T].view(B, T, d), x[B * T:].view(B, P, d)], 1)
+        return self._final_norm(x), torch.cat([txt_attn_masks, img_attn_masks], dim=1)
+
     def forward(self, img=None, txt=None, img_attn_masks=None, txt_attn_masks=None, fusion_layer=None,
                 img_token_type_idx=1):
         """Reference vlmo.py:415-434 (same positional order)."""

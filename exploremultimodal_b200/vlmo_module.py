@@ -7,6 +7,10 @@ keys, `infer` / `forward` / `load_from_ckpt` / `no_weight_decay` signatures and 
 Extra (optional) config fields, read with getattr so the reference's config tree works as is:
   config.model.precision : 'bf16' (default; the reference trains under fp16 autocast) | 'fp32'
   config.train.mlm_capacity : see objectives.compute_mlm
+  config.train.merge_passes : default True = independent sequences of different objectives share backbone passes
+                              (see _forward_objectives); False = one pass per reference `infer` call
+  config.train.dedup_prefix : True = compute the pre-fusion layers once per image / caption per step (see
+                              VlmoModule._encode_prefixes; exact without dropout; default False = reference passes)
 Not carried over (off in every BASELINE config): MIM / dVAE, MPP, NLVR2, IRTR
 heads, the momentum (EMA) teacher and the MoCo-style negative queue.
 """
@@ -63,6 +67,7 @@ class VlmoModule(nn.Module):
             self.vqa_classifier.apply(self.transformer._init_weights)
             self.vqa_last = None
         self.transformer_m = None
+        self._prefix = None
         self.q_size = 0
         self.img_queue, self.txt_queue = None, None
 
@@ -161,9 +166,23 @@ class VlmoModule(nn.Module):
             txt_ids = batch[f'text_ids{do_mlm}']
             txt_labels = batch[f'text_labels{do_mlm}'] if mask_txt else None
             txt_attn_masks = batch['text_mask']
-        co_feats, _ = transformer.forward_features(img=img, txt=txt_ids, img_attn_masks=img_attn_masks,
-                                                   txt_attn_masks=txt_attn_masks, bool_masked_pos=bool_masked_pos,
-                                                   fusion_layer=None)
+        pre = self._prefix
+        if pre is not None and not mask_img and image_token_type_idx == 1:
+            # de-duplicated pre-fusion layers (config.train.dedup_prefix): continue from the cached branches
+            idx = batch['_prefix_index'] if '_prefix_index' in batch else None
+            img_pre = txt_pre = None
+            if img is not None:
+                img_pre = pre['img'] if idx is None else pre['img'][idx[0]]
+            if txt_ids is not None:
+                txt_pre = pre['txt_mlm' if mask_txt else 'txt']
+                txt_pre = txt_pre if idx is None else txt_pre[idx[1]]
+            co_feats, _ = transformer.forward_features_from_prefix(img_pre=img_pre, txt_pre=txt_pre,
+                                                                   img_attn_masks=img_attn_masks,
+                                                                   txt_attn_masks=txt_attn_masks)
+        else:
+            co_feats, _ = transformer.forward_features(img=img, txt=txt_ids, img_attn_masks=img_attn_masks,
+                                                       txt_attn_masks=txt_attn_masks, bool_masked_pos=bool_masked_pos,
+                                                       fusion_layer=None)
         if txt_ids is not None:
             T = transformer.max_text_len
             txt_feats, img_feats = co_feats[:, :T], co_feats[:, T:]
@@ -175,6 +194,21 @@ class VlmoModule(nn.Module):
                 'img_masks': img_attn_masks, 'img_bool_masked_pos': bool_masked_pos, 'txt_labels': txt_labels,
                 'txt_ids': txt_ids, 'txt_masks': txt_attn_masks}
 
+    def infer_pair(self, batch):
+        """`infer(batch, 'img_only')` and `infer(batch, 'txt_only')` (what compute_itc needs, reference objectives.py:87-88)
+        as one packed backbone pass; returns the two result dicts (co_feats / cls_feats / masks)."""
+        T = self.transformer
+        img, txt_ids, txt_masks = batch['image'], batch['text_ids'], batch['text_mask']
+        img_masks = torch.ones([img.size(0), T.patch_embed.num_patches + 1], dtype=torch.int64, device=img.device)
+        img_feats, txt_feats = T.forward_features_pair(img, txt_ids, img_masks, txt_masks)
+        with T._autocast():
+            cls_i, cls_t = T.pooler(img_feats), T.pooler(txt_feats)
+        img_ret = {'txt_feats': None, 'img_feats': img_feats, 'co_feats': img_feats, 'cls_feats': cls_i, 'img_masks': img_masks,
+                   'img_bool_masked_pos': None, 'txt_labels': None, 'txt_ids': None, 'txt_masks': None}
+        txt_ret = {'txt_feats': txt_feats, 'img_feats': None, 'co_feats': txt_feats, 'cls_feats': cls_t, 'img_masks': None,
+                   'img_bool_masked_pos': None, 'txt_labels': None, 'txt_ids': txt_ids, 'txt_masks': txt_masks}
+        return img_ret, txt_ret
+
     # ---- reference vlmo_module.py:395-436
     def forward(self, batch):
         batch = defaultdict(lambda: None, batch)
@@ -184,7 +218,44 @@ class VlmoModule(nn.Module):
         if len(self.loss_names) == 0:
             ret.update(self.infer(batch))
             return ret
-        if 'mlm' in self.loss_names:
+        self._prefix = self._encode_prefixes(batch) if getattr(self.config.train, 'dedup_prefix', False) else None
+        try:
+            return self._forward_objectives(batch, ret)
+        finally:
+            self._prefix = None
+
+    def _encode_prefixes(self, batch):
+        """Opt-in (config.train.dedup_prefix): run blocks[:fusion_layer] ONCE per image, per
+        unmasked caption and per MLM-masked caption; the objectives' passes then start at the fusion layer (ITM
+        negatives gather rows of these). The reference recomputes them in every pass (vlmo.py:402-404)."""
+        T = self.transformer
+        pre = {}
+        names = set(self.loss_names)
+        img, txt_mask = batch['image'], batch['text_mask']
+        if img is not None:
+            ones = torch.ones([img.size(0), T.patch_embed.num_patches + 1], dtype=torch.int64, device=img.device)
+            pre['img'] = T.encode_prefix('v', img, ones)
+        if names & {'itc', 'itm', 'vqa'} and batch['text_ids'] is not None:
+            pre['txt'] = T.encode_prefix('l', batch['text_ids'], txt_mask)
+        if 'mlm' in names and batch['text_ids_mlm'] is not None:
+            pre['txt_mlm'] = T.encode_prefix('l', batch['text_ids_mlm'], txt_mask)
+        return pre
+
+    def _forward_objectives(self, batch, ret):
+        names = self.loss_names
+        # config.train.merge_passes (default on): independent sequences of different objectives share backbone passes —
+        # MLM + ITM positives + ITM negatives as one 4 B img-txt pass, ITC's two single-modality passes as one packed
+        # pass. Per-sequence math, losses and gradients are the reference's (objectives.compute_mlm_itm_merged).
+        merge = (getattr(self.config.train, 'merge_passes', True) and self._prefix is None and batch['image'] is not None
+                 and batch['text_ids_mlm'] is not None)
+        if merge and 'mlm' in names and 'itm' in names:
+            if 'itc' in names:
+                ret.update(objectives.compute_itc(self, batch))
+            ret.update(objectives.compute_mlm_itm_merged(self, batch, ret if 'itc' in names else None))
+            if 'vqa' in names:
+                ret.update(objectives.compute_vqa(self, batch))
+            return ret
+        if 'mlm' in names:
             ret.update(objectives.compute_mlm(self, batch))
         if 'itc' in self.loss_names:
             ret.update(objectives.compute_itc(self, batch))

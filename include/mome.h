@@ -116,8 +116,9 @@ typedef struct {
   const void* aux;   /* operand dtype [M, ldaux] (DGELU) */
   int64_t row0;      /* row of the packed token buffer this group starts at (dropout masks and row_scale are
                         indexed by that global row, so forward and backward agree however rows are grouped) */
-  float* colsum;     /* optional (STORE / DGELU), ZEROED fp32 [ceil(M/32), N]: row i receives the column sums of
-                        the stored out rows [32 i, 32 i + 32); mome_colreduce adds the rows (bias gradient) */
+  float* colsum;     /* optional (STORE / DGELU), fp32 [ceil(M/32), N]: row i receives the column sums of the stored out
+                        rows [32 i, 32 i + 32); mome_colreduce adds the rows (bias gradient). The bf16 path writes
+                        every element once; the fp32 validation path accumulates, so ZERO it there */
 } MomeGemmGroup;
 
 typedef struct {
@@ -213,7 +214,7 @@ typedef struct {
   const void* w2;            /* fc2.weight [d, hid]  (compute dtype) */
   const float* b2;           /* fc2.bias   [d] */
   float *dw1, *db1, *dw2, *db2; /* backward: gradient accumulators */
-  float* colsum_part;        /* backward scratch: ZEROED fp32 [ceil(rows / 32), hid] */
+  float* colsum_part;        /* backward scratch: fp32 [ceil(rows / 32), hid] (zeroed on the fp32 path, see MomeGemmGroup.colsum) */
 } MomeBlockGroup;
 
 typedef struct {

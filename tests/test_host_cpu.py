@@ -221,3 +221,20 @@ def test_gradsync_flat_buffers_back_every_gradient():
     torch.optim.SGD(model.parameters(), lr=0.1).zero_grad(set_to_none=False)
     assert float(sync.block_flat[1].sum()) == 0.0
     sync.finish()   # world 1: nothing to exchange
+
+
+def test_mlm_compaction_is_ordered_and_counts_overflow():
+    """objectives.compact_masked_rows: the first K masked rows in order, -100 padding, overflow counted (no host sync)."""
+    from exploremultimodal_b200.objectives import compact_masked_rows
+    g = torch.Generator().manual_seed(0)
+    lab = torch.full((400,), -100)
+    idx = torch.randperm(400, generator=g)[:37]
+    lab[idx] = torch.arange(37) + 5
+    want = torch.nonzero(lab != -100).flatten()
+    for cap in (64, 37, 20):
+        order, tgt, overflow = compact_masked_rows(lab, cap)
+        n = min(cap, 37)
+        assert torch.equal(order[:n], want[:n]) and torch.equal(tgt[:n], lab[want[:n]])
+        assert bool((tgt[n:] == -100).all()) and int(overflow) == max(0, 37 - cap)
+    order, tgt, overflow = compact_masked_rows(torch.full((16,), -100), 8)
+    assert bool((tgt == -100).all()) and int(overflow) == 0

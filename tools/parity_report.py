@@ -75,18 +75,21 @@ def main():
     ap.add_argument('--batch', type=int, default=3)
     ap.add_argument('--lengths', default='realistic')
     ap.add_argument('--init-values', type=float, default=None)
+    ap.add_argument('--vqa480', action='store_true', help='VQAv2 finetune step at 480^2 (BASELINE configs[3]) instead of MLM + ITC + ITM')
     ap.add_argument('--out', default=None)
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     kw = {} if a.init_values is None else {'init_values': a.init_values}
+    if a.vqa480:
+        kw.update(phase='finetune_vqa', loss_names=('vqa',), img_size=480)
     cfg = make_config(a.model, parity=True, **kw)
-    batch = {k: v.cuda() for k, v in make_batch(cfg, a.batch, seed=11, lengths=a.lengths).items()}
+    batch = {k: v.cuda() for k, v in make_batch(cfg, a.batch, seed=11, lengths=a.lengths, vqa=a.vqa480).items()}
     ref_l, ref_g = run_reference(cfg, batch, autocast=False)
     runs = {'ref_bf16': run_reference(cfg, batch, autocast=True),
             'mome_fp32': run_mome(cfg, batch, 'fp32'),
             'mome_bf16': run_mome(cfg, batch, 'bf16')}
-    report = {'model': a.model, 'batch': a.batch, 'lengths': a.lengths, 'init_values': cfg.model.init_values,
+    report = {'model': a.model, 'vqa480': a.vqa480, 'batch': a.batch, 'lengths': a.lengths, 'init_values': cfg.model.init_values,
               'ref_losses': ref_l, 'runs': {}}
     for name, (losses, grads) in runs.items():
         per = {}
