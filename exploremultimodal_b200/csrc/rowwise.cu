@@ -6,6 +6,8 @@
 //
 // Replaces: nn.LayerNorm / apex FusedLayerNorm (reference vlmo.py:26-36, 188-196, 413), the
 // LayerScale multiply-adds (vlmo.py:194-196) and their autograd backward.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "dropout.cuh"
@@ -164,7 +166,9 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
 // LayerNorm backward (+ residual gradient), optionally fused with the LayerScale backward of the branch
 // that produced this residual stream (FUSE): dbranch = gamma * dx, dgamma += sum dx * branch,
 // dbias_br += sum dbranch.
-template <typename InT, typename BrT, bool FUSE>
+// HOIST: the operands of the second phase (residual gradient, branch) are requested together with dy / x, before the
+// block reduction, so that an iteration costs one memory round trip instead of two.
+template <typename InT, typename BrT, bool FUSE, bool HOIST>
 __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ w, const float* __restrict__ dres,
@@ -186,13 +190,17 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
   float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ab = aw, ag = aw, abb = aw;
   int buf = 0;
   for (long long r0 = static_cast<long long>(blockIdx.x) * kLnRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kLnRows) {
-    float4 g[kLnRows], xh[kLnRows];
+    float4 g[kLnRows], xh[kLnRows], rsd[HOIST ? kLnRows : 1], brv[(HOIST && FUSE) ? kLnRows : 1];
     float rs[kLnRows], sums[2 * kLnRows];
 #pragma unroll
     for (int j = 0; j < kLnRows; ++j) {
       const long long row = r0 + j;
       g[j] = xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       rs[j] = 0.f;
+      if (HOIST && row < rows && active) {
+        rsd[j] = dres != nullptr ? load4(dres + row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FUSE) brv[j] = load4(branch + row * d + c);
+      }
       if (row < rows && active) {
         const float mu = __ldg(mean + row);
         rs[j] = __ldg(rstd + row);
@@ -219,13 +227,15 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
         o.y = rs[j] * (g[j].y - m1 - xh[j].y * m2);
         o.z = rs[j] * (g[j].z - m1 - xh[j].z * m2);
         o.w = rs[j] * (g[j].w - m1 - xh[j].w * m2);
-        if (dres != nullptr) {
+        if (HOIST) {
+          o.x += rsd[j].x; o.y += rsd[j].y; o.z += rsd[j].z; o.w += rsd[j].w;
+        } else if (dres != nullptr) {
           const float4 r = load4(dres + row * d + c);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         store4(dx + row * d + c, o);
         if (FUSE) {
-          const float4 br = load4(branch + row * d + c);
+          const float4 br = HOIST ? brv[j] : load4(branch + row * d + c);
           // x1 = x + gamma * row_scale * drop(branch): `br` is the stored dropped branch, bm = mask * scale * row_scale
           const float4 bm = branch_mul4(dd, dkey, dscale, row, d, c);
           float4 dbr = make_float4(o.x * gm.x * bm.x, o.y * gm.y * bm.y, o.z * gm.z * bm.z, o.w * gm.w * bm.w);
@@ -402,13 +412,18 @@ static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const flo
                          const float* dres, float* dx_out, float* dweight, float* dbias, const void* branch, const float* gamma,
                          void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, const DropDev& dd, float* ws,
                          cudaStream_t s) {
+  static const int variant = [] { const char* e = getenv("MOME_LN_BWD_VARIANT"); return e ? atoi(e) : 1; }();  // 0: two-phase loads
   const int threads = col_threads(d), grid = col_grid(rows, 5, kLnRows);
-  if (dy_dtype == MOME_BF16)
-    ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE><<<grid, threads, 0, s>>>(
+  if (dy_dtype == MOME_BF16 && variant == 0)
+    ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE, false><<<grid, threads, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
+        static_cast<__nv_bfloat16*>(dbranch), dd, ws, rows, (int)d);
+  else if (dy_dtype == MOME_BF16)
+    ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE, true><<<grid, threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
         static_cast<__nv_bfloat16*>(dbranch), dd, ws, rows, (int)d);
   else
-    ln_bwd_cols_kernel<float, float, FUSE><<<grid, threads, 0, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out,
+    ln_bwd_cols_kernel<float, float, FUSE, false><<<grid, threads, 0, s>>>(static_cast<const float*>(dy), x, mean, rstd, weight, dres, dx_out,
                                                                      static_cast<const float*>(branch), gamma,
                                                                      static_cast<float*>(dbranch), dd, ws, rows, (int)d);
   int rc = check_launch(FUSE ? "ln_bwd_scale" : "ln_bwd");

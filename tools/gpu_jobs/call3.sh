@@ -6,6 +6,8 @@ python -m pytest tests -m gpu -q > $O/r3_tests.log 2>&1; echo "tests rc=$?"; tai
 MOME_BUILD_CACHED=1 python __graft_entry__.py smoke > $O/r3_smoke.log 2>&1; echo "smoke rc=$?"; grep "smoke" $O/r3_smoke.log
 python tools/gemm_bench.py > $O/r3_gb.log 2>&1; cat $O/r3_gb.log
 MOME_GEMM_DEBUG=32 python tools/gemm_bench.py --only DGELU > $O/r3_gb_aux2.log 2>&1; cat $O/r3_gb_aux2.log
+MOME_LN_BWD_VARIANT=0 python tools/row_bench.py > $O/r3_row_v0.log 2>&1; cat $O/r3_row_v0.log
+MOME_LN_BWD_VARIANT=1 python tools/row_bench.py > $O/r3_row_v1.log 2>&1; cat $O/r3_row_v1.log
 python tools/attn_bench.py --check --tc-bwd 2 --iters 20 > $O/r3_attn_bwd2.log 2>&1; echo "attn tc-bwd=2 rc=$?"; tail -12 $O/r3_attn_bwd2.log
 python tools/attn_bench.py --tc-bwd 1 --iters 20 > $O/r3_attn_bwd1.log 2>&1; tail -8 $O/r3_attn_bwd1.log
 python bench.py --steps 10 --warmup 3 > $O/r3_bench_merged.log 2>&1; tail -c 300 $O/r3_bench_merged.log
