@@ -7,6 +7,8 @@
 //
 // Replaces: reference heads.py:125-126 (F.normalize), objectives.py:99-108 / 166-171 (logits),
 // objectives.py:173-180 (cross-entropy, accuracy) and their autograd backward.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "vec.cuh"
@@ -379,4 +381,31 @@ extern "C" int mome_itc_bwd_peer(const float* i_feat, const float* t_feat, const
   const ColSrc src{nullptr, nullptr, static_cast<const float* const*>(peers), bs, dim};
   return itc_bwd_launch(i_feat, t_feat, src, temp, bs, world, rank, dim, lse, gscale, d_i_feat, d_t_feat, d_all_i, d_all_t, d_temp,
                         static_cast<cudaStream_t>(stream));
+}
+
+// Cross-rank gather over NVLink, once per step: all_i / all_t [world * bs, dim] <- every rank's symmetric
+// [2, bs, dim] buffer, read with 128-bit peer loads (GatherLayer.forward's all_gather + cat, objectives.py:401-414).
+// Every remote element crosses NVLink exactly once (2 * (world - 1) * bs * dim * 4 bytes per rank), instead of once
+// per CTA of the similarity kernel as in the *_peer variants above.
+__global__ void __launch_bounds__(256) itc_gather_peer_kernel(const float* const* __restrict__ peers, float* __restrict__ all_i,
+                                                              float* __restrict__ all_t, int bs, int dim, int world) {
+  const long long per_rank = static_cast<long long>(bs) * dim / 4;  // float4 per modality per rank
+  const long long total = 2LL * world * per_rank;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int sel = static_cast<int>(v / (world * per_rank));
+    const long long w = v - sel * world * per_rank;
+    const int r = static_cast<int>(w / per_rank);
+    const long long e = w - r * per_rank;
+    const float4 val = reinterpret_cast<const float4*>(peers[r])[sel * per_rank + e];
+    reinterpret_cast<float4*>(sel == 0 ? all_i : all_t)[r * per_rank + e] = val;
+  }
+}
+
+extern "C" int mome_itc_gather_peer(const void* peers, int32_t bs, int32_t world, int32_t dim, float* all_i, float* all_t, void* stream) {
+  MOME_REQUIRE(peers != nullptr && all_i != nullptr && all_t != nullptr, "itc_gather_peer: null argument");
+  MOME_REQUIRE(bs >= 1 && world >= 1 && dim % 4 == 0, "itc_gather_peer: need bs, world >= 1 and dim %% 4 == 0");
+  const long long total = 2LL * world * bs * dim / 4;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 2LL * sm_count())));
+  itc_gather_peer_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float* const*>(peers), all_i, all_t, bs, dim, world);
+  return check_launch("itc_gather_peer");
 }

@@ -7,6 +7,8 @@ logit matrices are never materialised (only the local [bs, bs] blocks ITM needs 
 MLM / ITM / VQA are callers of the backbone kept in stock PyTorch like the reference, but written
 without the reference's per-step host synchronisations (boolean-mask indexing, `.item()` loops).
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -94,7 +96,6 @@ class _PeerGather:
 
     @classmethod
     def get(cls, bs, dim, device):
-        import os
         mode = os.environ.get('MOME_ITC_GATHER', 'peer')
         if mode not in ('peer', 'nccl', 'auto'):
             raise ValueError(f'MOME_ITC_GATHER={mode!r}: expected peer, nccl or auto')
@@ -148,7 +149,11 @@ class _ItcFn(torch.autograd.Function):
         sim_local = torch.empty(2, bs, bs, dtype=torch.float32, device=dev)
         peer = _PeerGather.get(bs, dim, dev) if world > 1 else None
         ctx.peer = peer
-        if peer is not None:
+        direct = peer is not None and os.environ.get('MOME_ITC_PEER_DIRECT') == '1'
+        ctx.direct = direct
+        if direct:
+            # every CTA of the similarity kernel loads the remote rows itself (W * bs * dim * 4 bytes per CTA over
+            # NVLink: fine for small bs, 100 x the algorithmic bytes at bs = 512; kept for comparison)
             buf, hdl = peer
             hdl.barrier(channel=0)       # every rank is done reading the previous step's features (fwd and bwd)
             buf[0].copy_(i_feat)
@@ -158,6 +163,21 @@ class _ItcFn(torch.autograd.Function):
                                               bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
                                               lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd_peer')
             all_i = all_t = i_feat  # placeholders (the backward reads the peers' buffers again)
+        elif peer is not None:
+            # own gather kernel: each remote [bs, dim] block crosses NVLink once (peer loads), then the fused
+            # similarity + cross-entropy kernel runs on the local copy; the backward reuses that copy
+            buf, hdl = peer
+            hdl.barrier(channel=0)       # every rank has finished gathering the previous step's features
+            buf[0].copy_(i_feat)
+            buf[1].copy_(t_feat)
+            hdl.barrier(channel=1)       # every rank's features are in place
+            all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=dev)
+            all_t = torch.empty_like(all_i)
+            L.check(L.lib().mome_itc_gather_peer(hdl.buffer_ptrs_dev, bs, world, dim, all_i.data_ptr(), all_t.data_ptr(),
+                                                 L.stream()), 'mome_itc_gather_peer')
+            L.check(L.lib().mome_itc_fwd(i_feat.data_ptr(), t_feat.data_ptr(), all_i.data_ptr(), all_t.data_ptr(),
+                                         temp.data_ptr(), bs, world, rank, dim, loss_sum.data_ptr(), correct.data_ptr(),
+                                         lse.data_ptr(), sim_local.data_ptr(), L.stream()), 'mome_itc_fwd')
         else:
             if world > 1:
                 all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=dev)
@@ -186,7 +206,7 @@ class _ItcFn(torch.autograd.Function):
         d_all_i = torch.empty(world * bs, dim, dtype=torch.float32, device=dev)
         d_all_t = torch.empty_like(d_all_i)
         d_temp = torch.zeros(1, dtype=torch.float32, device=dev)
-        if ctx.peer is not None:
+        if ctx.peer is not None and ctx.direct:
             L.check(L.lib().mome_itc_bwd_peer(i_feat.data_ptr(), t_feat.data_ptr(), ctx.peer[1].buffer_ptrs_dev,
                                               temp.data_ptr(), bs, world, rank, dim, lse.data_ptr(), g.data_ptr(),
                                               d_i.data_ptr(), d_t.data_ptr(), d_all_i.data_ptr(), d_all_t.data_ptr(),

@@ -198,6 +198,11 @@ int mome_itc_bwd_peer(const float* i_feat, const float* t_feat, const void* peer
                       int32_t world, int32_t rank, int32_t dim, const float* lse, const float* gscale, float* d_i_feat,
                       float* d_t_feat, float* d_all_i, float* d_all_t, float* d_temp, void* stream);
 
+/* The cross-rank gather on its own: all_i / all_t [world*bs, dim] <- peers[r] (rank r's [2, bs, dim] buffer), 128-bit
+ * peer loads over NVLink, every remote element read once (reference GatherLayer.forward, objectives.py:401-414:
+ * all_gather + cat). Followed by mome_itc_fwd / mome_itc_bwd on the gathered arrays. */
+int mome_itc_gather_peer(const void* peers, int32_t bs, int32_t world, int32_t dim, float* all_i, float* all_t, void* stream);
+
 /* ---- One whole MoME block per call ------------------------------------------------------------------
  * reference: Block.forward, vlmo.py:187-197, and its autograd backward. These two entry points only
  * sequence the kernels above (7 launches forward, 14 backward) in native code, so that a host language

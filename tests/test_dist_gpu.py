@@ -1,5 +1,7 @@
 """GPU, world_size 2 (skipped with fewer than 2 GPUs): the NCCL / NVLink ITC path against the single-process
-full-batch loss (SURVEY.md 3.3 identity), for both the in-kernel peer gather and the NCCL all_gather variant."""
+full-batch loss (SURVEY.md 3.3 identity), for the NVLink peer gather kernel (`peer`), the similarity kernel loading remote rows itself (`peer_direct`) and the
+NCCL all_gather variant. A second test runs whole training steps on 2 ranks and checks that GradSync leaves every rank with
+bit-identical gradients equal to the full-batch gradient."""
 import os
 import socket
 
@@ -23,7 +25,8 @@ def _free_port():
 def _worker(rank, world, port, bs, dim, mode, out):
     import sys
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), MOME_ITC_GATHER=mode)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), MOME_ITC_GATHER='peer' if mode == 'peer_direct' else mode,
+                      MOME_ITC_PEER_DIRECT='1' if mode == 'peer_direct' else '0')
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -40,7 +43,7 @@ def _worker(rank, world, port, bs, dim, mode, out):
         ret['itc_task_loss'].backward()
         res.append(dict(loss=ret['itc_task_loss'].detach().cpu(), gi=mi.grad.cpu(), gt=mt.grad.cpu(),
                         sim=ret['sim_i2t'].detach().cpu(), acc=ret['itc_i2t_mean_acc'].cpu()))
-    if mode == 'peer':  # the NVLink path really ran (no silent NCCL substitute)
+    if mode in ('peer', 'peer_direct'):  # the NVLink path really ran (no silent NCCL substitute)
         assert objectives._PeerGather._cache and all(v is not None for v in objectives._PeerGather._cache.values())
     torch.cuda.synchronize()
     torch.save(res, os.path.join(out, f'r{rank}.pt'))
@@ -48,7 +51,7 @@ def _worker(rank, world, port, bs, dim, mode, out):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize('mode', ['peer', 'nccl'])
+@pytest.mark.parametrize('mode', ['peer', 'peer_direct', 'nccl'])
 def test_itc_two_ranks_equals_full_batch(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -71,3 +74,69 @@ def test_itc_two_ranks_equals_full_batch(tmp_path, mode):
         assert (gi - fi.grad).norm() / fi.grad.norm() < 1e-4
         assert (gt - ft.grad).norm() / ft.grad.norm() < 1e-4
         assert torch.allclose(parts[1][step]['sim'], full['sim_i2t'][bs:, bs:].detach(), atol=1e-3)
+
+
+def _grad_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from exploremultimodal_b200 import build_model, make_config, objectives
+    from exploremultimodal_b200.ddp import GradSync
+    from exploremultimodal_b200.synthetic import make_batch, synth_state_dict
+    cfg = make_config('vlmo_unit', parity=True, global_reduce=True)
+    cfg.model.precision = 'fp32'
+    model = build_model(cfg)
+    shapes = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(synth_state_dict(shapes, cfg.model.init_values))
+    model.cuda().train()
+    model.itm_negative_picker = objectives.pick_negatives_argmax
+    sync = GradSync(model, world)
+    full = make_batch(cfg, 4 * world, seed=5, lengths='full')
+    mine = {k: v[rank * 4:(rank + 1) * 4].cuda() for k, v in full.items()}
+    for step in range(2):
+        sync.zero_grad()
+        out_d = model(mine)
+        # ITM mines negatives inside the local batch only (objectives.py:254-255): leave it out so that the
+        # rank-mean of the loss is the full-batch loss and gradients are comparable
+        loss = out_d['mlm_task_loss'] + out_d['itc_task_loss']
+        loss.backward()
+        sync.finish()
+    torch.cuda.synchronize()
+    torch.save({k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}, os.path.join(out, f'g{rank}.pt'))
+    os._exit(0)
+
+
+@pytest.mark.timeout(300)
+def test_gradsync_two_ranks_bit_identical_and_equal_to_full_batch(tmp_path):
+    """the per-block all-reduce must see FINAL gradients of every parameter (q_bias / v_bias included).
+    Every rank ends with bit-identical .grad, equal to the mean of the per-rank gradients = the full-batch gradient of
+    (MLM + ITC) computed by the CPU oracle on the concatenated batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from helpers import oracle_state
+    from exploremultimodal_b200 import make_config
+    from exploremultimodal_b200.synthetic import make_batch
+    from oracle import mome_oracle as O
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = [torch.load(tmp_path / f'g{r}.pt') for r in range(world)]
+    assert set(g[0]) == set(g[1])
+    for k in g[0]:
+        assert torch.equal(g[0][k], g[1][k]), f'{k}: ranks hold different gradients'
+    cfg = make_config('vlmo_unit', parity=True)
+    sd = oracle_state(cfg)
+    full = make_batch(cfg, 4 * world, seed=5, lengths='full')
+    ret = O.module_forward(sd, cfg, full)
+    (ret['mlm_task_loss'] + ret['itc_task_loss']).backward()
+    bad = []
+    for k, v in g[0].items():
+        ref = sd[k].grad if k in sd else None
+        if ref is None or float(ref.norm()) == 0.0:
+            continue
+        err = float((v.double() - ref.double()).norm() / ref.double().norm())
+        if err > 2e-4:
+            bad.append((k, err))
+    assert not bad, bad[:8]
