@@ -318,16 +318,26 @@ def block_route_tflops(model, cfg, B, dev, iters=10):
         def run():
             y, _ = blk(x, mask, route)
             y.backward(g)
-        for _ in range(3):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()   # one forward + backward, replayed: device time without host launch gaps
+        with torch.cuda.graph(graph):
             run()
+        graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            run()
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
+        del graph
         out[route] = {'tokens_per_seq': N, 'seqs': B, 'ms_fwd_bwd': ms,
                       'tflops': 3 * flops.block_forward(m.embed_dim, N) * B / (ms * 1e-3) / 1e12}
     for p in blk.parameters():

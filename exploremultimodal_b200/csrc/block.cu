@@ -140,9 +140,8 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   MOME_TRY(mome_attn_bwd(a->qkv, a->o, a->s_do, dt, a->seq_desc, a->key_mask, a->lse, a->s_dqkv, a->s_delta, T, a->num_seqs,
                          a->max_seq_len, a->num_heads, a->scale, on(a, a->p_attn) ? a->drop_seed : nullptr, a->drop_salt, a->p_attn, stream));
   // q_bias / v_bias gradients: column sums of the q and v thirds of dqkv (the k third has no bias, vlmo.py:72-75)
-  if (a->dq_bias != nullptr) MOME_TRY(mome_colsum(a->s_dqkv, dt, T, d, 3 * d, a->dq_bias, a->ws, a->ws_bytes, stream));
-  if (a->dv_bias != nullptr)
-    MOME_TRY(mome_colsum(at(a->s_dqkv, 0, 0, es) + 2 * d * es, dt, T, d, 3 * d, a->dv_bias, a->ws, a->ws_bytes, stream));
+  if (a->dq_bias != nullptr && a->dv_bias != nullptr)
+    MOME_TRY(mome::colsum_qv(a->s_dqkv, dt, T, d, a->dq_bias, a->dv_bias, a->ws, a->ws_bytes, static_cast<cudaStream_t>(stream)));
   {
     MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, 3 * d, d, d);
     g.group[0].a = a->s_dqkv; g.group[0].b = a->h; g.group[0].M = 3 * d; g.group[0].K = T; g.group[0].out = a->dw_qkv;

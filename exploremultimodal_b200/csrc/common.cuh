@@ -31,6 +31,10 @@ inline int check_launch(const char* what) {
     }                                \
   } while (0)
 
+// rowwise.cu: column sums of the q and v thirds of dqkv (used by block.cu)
+int colsum_qv(const void* dqkv, int dtype, int64_t rows, int64_t d, float* dq_bias, float* dv_bias, void* ws, size_t ws_bytes,
+              cudaStream_t s);
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

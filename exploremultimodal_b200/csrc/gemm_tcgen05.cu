@@ -38,8 +38,12 @@ constexpr int PAIR_M = 256;   // rows of a work item (two CTAs x 128)
 constexpr int CTA_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+// Epilogue warps per CTA. The MMAs of a K = 768 tile take ~8k cycles; with 8 epilogue warps (2 per scheduler) the
+// fused epilogues ran at ~0.2 IPC per warp (dependent chains, little to overlap them with) and took ~13k cycles per
+// tile (ncu r02: neither the tensor pipe nor issue slots saturated). Sixteen warps give each scheduler four to
+// interleave. RESIDUAL keeps 8: it holds the fp32 residual prefetch in registers and is HBM-bound at K = 768 anyway.
+constexpr int epi_warps(int epi) { return (epi == MOME_EPI_STORE || epi == MOME_EPI_GELU || epi == MOME_EPI_DGELU) ? 16 : 8; }
+constexpr int gemm_threads(int epi) { return 128 + 32 * epi_warps(epi); }
 constexpr int kAtomBytes = BLOCK_K * 128;  // one 64x64 MN-major box / 64 rows of a K-major tile
 constexpr int kStagePitch = 36;            // floats per row of the per-warp transpose tile (32 + pad, 16 B aligned)
 constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
@@ -142,20 +146,25 @@ __device__ __forceinline__ void gelu_fast2(float z0, float z1, float m0, float m
   dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EW>
 struct GemmCfg {
   static constexpr int A_BYTES = CTA_M * 128;            // this CTA's 128 rows x 64 k
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;    // this CTA's half of the N tile x 64 k
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 5 : 7;
+  // the ring shares the 227 KB with one transpose tile per epilogue warp
+  static constexpr int STAGES = (BLOCK_N == 256) ? (EW == 16 ? 4 : 5) : (EW == 16 ? 6 : 7);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int EPI_BYTES = kEpiWarps * kStageBytesPerWarp;
+  static constexpr int EPI_BYTES = EW * kStageBytesPerWarp;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DROP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int kEpiWarps = epi_warps(EPI);
+  constexpr int kParts = kEpiWarps / 4;            // column parts of a tile (one per group of 4 warps = 128 TMEM lanes)
+  constexpr int kPartCols = BLOCK_N / kParts;
+  using Cfg = GemmCfg<BLOCK_N, kEpiWarps>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -278,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which half of the tile's columns
+    const int part = ew >> 2;              // which column part of the tile
     const uint32_t stage_u32 = smem_u32(epi_stage + ew * (kStageBytesPerWarp / 4));  // this warp's transpose tile
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int acc = 0;
@@ -290,8 +299,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
       // number of this lane's 8 row-iterations that fall inside the group
       const GemmGroupDev g = p.g[w.g];
       const long long row0 = static_cast<long long>(w.m_tile) * PAIR_M + cta_rank * CTA_M + quarter * 32;
-      constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
-      const int col_base = w.n_tile * BLOCK_N + half * (BLOCK_N / 2) + c4;
+      constexpr int kChunks = kPartCols / 32;  // 32-column chunks per warp
+      const int col_base = w.n_tile * BLOCK_N + part * kPartCols + c4;
       const long long rfirst = row0 + rsub;
       const int nvalid = static_cast<int>(max(0LL, min(8LL, (static_cast<long long>(g.M) - rfirst + 3) >> 2)));
       const int nchunks = max(0, min(kChunks, (p.N - col_base + 31) >> 5));  // chunks inside N (N % 32 == 0)
@@ -315,10 +324,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- operands the epilogue reads besides the accumulator are requested BEFORE the wait for the MMAs:
         // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
-        // lane-iteration): the first chunks up front (three for gelu', two for the residual), then that many chunks ahead
-        // of their use (ncu: with two, the gelu' loads of chunks 2 and 3 still stalled their first use on the long scoreboard).
-        constexpr int kAuxWant = DROP ? 3 : 2;  // DGELU has no dropout of its own: the flag selects the prefetch depth (measurement)
-        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < kAuxWant ? kChunks : kAuxWant) : 1;
+        // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use (three deep was measured:
+        // 908 against 921 TFLOP/s, the extra registers cost more than the loads' exposed latency).
+        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks <= 2 ? 1 : 2) : 1;  // 16 epilogue warps: one chunk ahead, 96 registers
         constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
         uint2 aux[kAuxDepth][8];
         float4 res[kResDepth][8];
@@ -345,7 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_pa
 
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + part * kPartCols;
   #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           uint32_t r[32];
@@ -523,7 +531,7 @@ std::vector<ProfRec> g_prof;
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DROP = false>
 int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, epi_warps(EPI)>;
   static bool configured = false;
   auto kern = gemm_pair_kernel<BLOCK_N, A_MN, B_MN, EPI, DROP>;
   if (!configured) {
@@ -534,7 +542,7 @@ int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
     }
     configured = true;
   }
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, gemm_threads(EPI), Cfg::SMEM_BYTES, stream>>>(p);
   return check_launch("gemm_pair");
 }
 
@@ -555,9 +563,7 @@ int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, int grid, cudaStream_
   } else if (!a_mn && b_mn) {
     switch (p.epilogue) {
       case MOME_EPI_STORE: return launch_one<BLOCK_N, false, true, MOME_EPI_STORE>(p, grid, stream);
-      case MOME_EPI_DGELU:
-        return (p.debug & 32) ? launch_one<BLOCK_N, false, true, MOME_EPI_DGELU, false>(p, grid, stream)
-                              : launch_one<BLOCK_N, false, true, MOME_EPI_DGELU, true>(p, grid, stream);
+      case MOME_EPI_DGELU: return launch_one<BLOCK_N, false, true, MOME_EPI_DGELU>(p, grid, stream);
       case MOME_EPI_ATOMIC: return launch_one<BLOCK_N, false, true, MOME_EPI_ATOMIC>(p, grid, stream);
     }
   } else if (a_mn && b_mn) {

@@ -8,6 +8,8 @@
 // LayerScale multiply-adds (vlmo.py:194-196) and their autograd backward.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "dropout.cuh"
@@ -98,6 +100,16 @@ __device__ __forceinline__ float4 branch_mul4(const DropDev& dd, uint32_t key, f
   return m;
 }
 
+// same with the row's stochastic-depth multiplier already loaded (requested together with the row's other operands)
+__device__ __forceinline__ float4 branch_mul4_rs(const DropDev& dd, uint32_t key, float scale, long long r, int d, int c, float rs) {
+  float4 m = make_float4(rs, rs, rs, rs);
+  if (dd.seed != nullptr) {
+    const float4 k = drop_mul4(drop_group(dd.row0 + r, d, c), key, dd.thr, scale);
+    m.x *= k.x; m.y *= k.y; m.z *= k.z; m.w *= k.w;
+  }
+  return m;
+}
+
 constexpr int kColRows = 4;   // rows per iteration (LayerScale backward)
 constexpr int kLnRows = 2;    // rows per iteration (LayerNorm backward: keeps registers low enough for 5-6 CTAs / SM)
 
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
 // HOIST: the operands of the second phase (residual gradient, branch) are requested together with dy / x, before the
 // block reduction, so that an iteration costs one memory round trip instead of two.
 template <typename InT, typename BrT, bool FUSE, bool HOIST>
-__global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) ln_bwd_cols_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ w, const float* __restrict__ dres,
                                                           float* __restrict__ dx,
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
   int buf = 0;
   for (long long r0 = static_cast<long long>(blockIdx.x) * kLnRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kLnRows) {
     float4 g[kLnRows], xh[kLnRows], rsd[HOIST ? kLnRows : 1], brv[(HOIST && FUSE) ? kLnRows : 1];
-    float rs[kLnRows], sums[2 * kLnRows];
+    float rs[kLnRows], sums[2 * kLnRows], rowsc[(HOIST && FUSE) ? kLnRows : 1];
 #pragma unroll
     for (int j = 0; j < kLnRows; ++j) {
       const long long row = r0 + j;
@@ -200,6 +212,7 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
       if (HOIST && row < rows && active) {
         rsd[j] = dres != nullptr ? load4(dres + row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (FUSE) brv[j] = load4(branch + row * d + c);
+        if (FUSE) rowsc[j] = dd.row_scale != nullptr ? __ldg(dd.row_scale + dd.row0 + row) : 1.f;
       }
       if (row < rows && active) {
         const float mu = __ldg(mean + row);
@@ -237,12 +250,13 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_cols_kernel(const InT* __restri
         if (FUSE) {
           const float4 br = HOIST ? brv[j] : load4(branch + row * d + c);
           // x1 = x + gamma * row_scale * drop(branch): `br` is the stored dropped branch, bm = mask * scale * row_scale
-          const float4 bm = branch_mul4(dd, dkey, dscale, row, d, c);
+          float rs = 1.f;
+          if (HOIST) rs = rowsc[j];
+          else if (dd.row_scale != nullptr) rs = __ldg(dd.row_scale + dd.row0 + row);
+          const float4 bm = branch_mul4_rs(dd, dkey, dscale, row, d, c, rs);
           float4 dbr = make_float4(o.x * gm.x * bm.x, o.y * gm.y * bm.y, o.z * gm.z * bm.z, o.w * gm.w * bm.w);
           store4(dbranch + row * d + c, dbr);
           if (sizeof(BrT) == 2) dbr = bf16_round4(dbr);  // the bias gradient sums what the bf16 consumer sees
-          float rs = 1.f;
-          if (dd.row_scale != nullptr) rs = __ldg(dd.row_scale + dd.row0 + row);
           ag.x += o.x * br.x * rs; ag.y += o.y * br.y * rs; ag.z += o.z * br.z * rs; ag.w += o.w * br.w * rs;
           abb.x += dbr.x; abb.y += dbr.y; abb.z += dbr.z; abb.w += dbr.w;
         }
@@ -275,23 +289,25 @@ __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __rest
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
   for (long long r0 = static_cast<long long>(blockIdx.x) * kColRows; r0 < rows; r0 += static_cast<long long>(gridDim.x) * kColRows) {
     float4 g[kColRows], br[kColRows];
+    float rsv[kColRows];
 #pragma unroll
     for (int j = 0; j < kColRows; ++j) {
       g[j] = br[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rsv[j] = 1.f;
       if (r0 + j < rows) {
         g[j] = load4(dx + (r0 + j) * d + c);
         if (need_dgamma) br[j] = load4(branch + (r0 + j) * d + c);
+        if (dd.row_scale != nullptr) rsv[j] = __ldg(dd.row_scale + dd.row0 + r0 + j);
       }
     }
 #pragma unroll
     for (int j = 0; j < kColRows; ++j) {
       if (r0 + j < rows) {
-        const float4 bm = branch_mul4(dd, dkey, dscale, r0 + j, d, c);
+        const float rs = rsv[j];
+        const float4 bm = branch_mul4_rs(dd, dkey, dscale, r0 + j, d, c, rs);
         float4 o = make_float4(g[j].x * gm.x * bm.x, g[j].y * gm.y * bm.y, g[j].z * gm.z * bm.z, g[j].w * gm.w * bm.w);
         store4(dbranch + (r0 + j) * d + c, o);
         if (sizeof(BrT) == 2) o = bf16_round4(o);
-        float rs = 1.f;
-        if (dd.row_scale != nullptr) rs = __ldg(dd.row_scale + dd.row0 + r0 + j);
         ag.x += g[j].x * br[j].x * rs; ag.y += g[j].y * br[j].y * rs; ag.z += g[j].z * br[j].z * rs; ag.w += g[j].w * br[j].w * rs;
         ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
       }
@@ -304,11 +320,13 @@ __global__ void __launch_bounds__(256) scale_bwd_cols_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------- column sums
 // ws[by][j] = sum over the CTA's rows of x[r, j]; CTA (bx, by): 1024 columns x every gridDim.y-th group of 8 rows.
+// `gap_at` / `gap`: columns >= gap_at are read `gap` columns further right (q and v thirds of dqkv in one launch).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
-                                                     float* __restrict__ ws) {
+                                                     float* __restrict__ ws, int gap_at, int gap) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
+  x += (c >= gap_at ? gap : 0);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long r0 = static_cast<long long>(blockIdx.y) * 8; r0 < rows; r0 += static_cast<long long>(gridDim.y) * 8) {
     float4 v[8];
@@ -413,7 +431,17 @@ static int ln_bwd_launch(const void* dy, int dy_dtype, const float* x, const flo
                          void* dbranch, float* dgamma, float* dbias_br, int64_t rows, int64_t d, const DropDev& dd, float* ws,
                          cudaStream_t s) {
   static const int variant = [] { const char* e = getenv("MOME_LN_BWD_VARIANT"); return e ? atoi(e) : 1; }();  // 0: two-phase loads
-  const int threads = col_threads(d), grid = col_grid(rows, 5, kLnRows);
+  const int threads = col_threads(d);
+  // persistent grid = exactly the CTAs that are resident at once (a partial second wave would start late and finish last)
+  int per_sm = 4;
+  {
+    const void* fn = dy_dtype != MOME_BF16 ? reinterpret_cast<const void*>(&ln_bwd_cols_kernel<float, float, FUSE, false>)
+                     : variant == 0      ? reinterpret_cast<const void*>(&ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE, false>)
+                                         : reinterpret_cast<const void*>(&ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE, true>);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) == cudaSuccess && occ > 0) per_sm = std::min(occ, 6);
+  }
+  const int grid = col_grid(rows, per_sm, kLnRows);
   if (dy_dtype == MOME_BF16 && variant == 0)
     ln_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, FUSE, false><<<grid, threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, weight, dres, dx_out, static_cast<const __nv_bfloat16*>(branch), gamma,
@@ -488,14 +516,38 @@ extern "C" int mome_colsum(const void* x, int dtype, int64_t rows, int64_t cols,
   MOME_REQUIRE_WS("colsum", static_cast<size_t>(slabs) * cols * sizeof(float));
   float* w = static_cast<float*>(ws);
   if (dtype == MOME_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, w);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, (int)cols, ld, w, (int)cols, 0);
   else
-    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, w);
+    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, (int)cols, ld, w, (int)cols, 0);
   int rc = check_launch("colsum");
   if (rc != MOME_OK) return rc;
   ColOuts o{{out, nullptr, nullptr, nullptr}, (int)cols};
   return colreduce_launch(w, (int)slabs, (int)cols, o, s);
 }
+
+// dq_bias[j] += sum_r dqkv[r, j], dv_bias[j] += sum_r dqkv[r, 2 d + j]: the q and v thirds of dqkv [rows, 3 d] in one pass
+// (the k third has no bias, reference vlmo.py:72-75). Internal to the block sequencer (csrc/block.cu).
+namespace mome {
+int colsum_qv(const void* dqkv, int dtype, int64_t rows, int64_t d, float* dq_bias, float* dv_bias, void* ws, size_t ws_bytes,
+              cudaStream_t s) {
+  MOME_REQUIRE(d % 4 == 0, "colsum_qv: d must be a multiple of 4");
+  if (rows == 0) return MOME_OK;
+  const int cols = static_cast<int>(2 * d);
+  dim3 grid(static_cast<unsigned>((cols + 1023) / 1024), 1);
+  const long long slabs = std::max<long long>(1, std::min<long long>((rows + 7) / 8, (6LL * sm_count() + grid.x - 1) / grid.x));
+  grid.y = static_cast<unsigned>(slabs);
+  MOME_REQUIRE_WS("colsum_qv", static_cast<size_t>(slabs) * cols * sizeof(float));
+  float* w = static_cast<float*>(ws);
+  if (dtype == MOME_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dqkv), rows, cols, 3 * d, w, (int)d, (int)d);
+  else
+    colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(dqkv), rows, cols, 3 * d, w, (int)d, (int)d);
+  int rc = check_launch("colsum_qv");
+  if (rc != MOME_OK) return rc;
+  ColOuts o{{dq_bias, dv_bias, nullptr, nullptr}, (int)d};
+  return colreduce_launch(w, (int)slabs, cols, o, s);
+}
+}  // namespace mome
 
 extern "C" int mome_droppath_scales(const int32_t* row_sample, int64_t rows, const uint32_t* seed, uint32_t salt, float p, float* out,
                                     void* stream) {

@@ -24,10 +24,18 @@ import torch.distributed as dist
 
 class GradSync:
 
-    def __init__(self, model, world, reduce_dtype='fp32'):
-        assert reduce_dtype in ('fp32', 'bf16')
+    def __init__(self, model, world, reduce_dtype='fp32', reduce='all_reduce', flatten_params=False):
+        """reduce: 'all_reduce' (DDP: every rank ends with the mean gradient) or 'reduce_scatter' (ZeRO-2: rank r ends
+        with the mean of elements [r n / W, (r + 1) n / W) of every flat buffer only; the rest of the buffer is scratch).
+        flatten_params: also move every parameter's storage into a flat fp32 buffer per block (optim.FlatAdamW)."""
+        assert reduce_dtype in ('fp32', 'bf16') and reduce in ('all_reduce', 'reduce_scatter')
+        assert not (reduce == 'reduce_scatter' and reduce_dtype != 'fp32')
         self.world = world
+        self.rank = dist.get_rank() if (world > 1 and dist.is_initialized()) else 0
         self.reduce_dtype = reduce_dtype
+        self.reduce = reduce
+        self.flatten_params = flatten_params
+        self._sets = []           # (flat grad, flat param or None, params) per buffer
         cuda = next(model.parameters()).is_cuda
         self.comm = torch.cuda.Stream() if (world > 1 and cuda) else None  # CPU (gloo, tests): reduce inline
         in_block = set()
@@ -51,16 +59,31 @@ class GradSync:
 
     def _flatten(self, ps):
         if not ps:
+            self._sets.append((None, None, ps))
             return None
-        flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+        n = sum(p.numel() for p in ps)
+        pad = 4 * self.world                      # shards of equal size whose starts stay 16-byte aligned
+        n_pad = (n + pad - 1) // pad * pad
+        flat = torch.zeros(n_pad, dtype=torch.float32, device=ps[0].device)
+        flat_p = torch.zeros(n_pad, dtype=torch.float32, device=ps[0].device) if self.flatten_params else None
         off = 0
         for p in ps:
             view = flat[off:off + p.numel()].view_as(p)
             p.grad = view
             self._views.append((p, view))
             self._view_of[id(p)] = view
+            if flat_p is not None:
+                with torch.no_grad():
+                    pv = flat_p[off:off + p.numel()].view_as(p)
+                    pv.copy_(p.detach())
+                    p.data = pv
             off += p.numel()
+        self._sets.append((flat, flat_p, ps))
         return flat
+
+    def flat_sets(self):
+        """(flat gradient buffer, flat parameter buffer or None, parameters) per buffer: blocks first, then the rest."""
+        return list(self._sets)
 
     def zero_grad(self):
         for flat in self.block_flat + [self.rest_flat]:
@@ -70,6 +93,10 @@ class GradSync:
             p.grad = view
 
     def _all_reduce(self, flat):
+        if self.reduce == 'reduce_scatter':
+            n = flat.numel() // self.world
+            dist.reduce_scatter_tensor(flat[self.rank * n:(self.rank + 1) * n], flat, op=dist.ReduceOp.AVG)  # in place
+            return
         if self.reduce_dtype == 'bf16':
             low = flat.to(torch.bfloat16)
             dist.all_reduce(low, op=dist.ReduceOp.AVG)

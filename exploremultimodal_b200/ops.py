@@ -53,11 +53,19 @@ class PackedLayout:
         return [(r, s, n) for (s, n, r) in self.groups]
 
 
+_SINGLE = {}
+
+
 def single_layout(B, N, route, device):
-    """B sequences of N tokens, one modality / one expert (reference Block.forward as called)."""
-    b = torch.arange(B, dtype=torch.int32)
-    desc = torch.stack([b * N, torch.full_like(b, N), torch.zeros_like(b), torch.zeros_like(b)], 1)
-    return PackedLayout(B * N, [(0, B * N, route)], desc.contiguous().to(device), B, N)
+    """B sequences of N tokens, one modality / one expert (reference Block.forward as called). Cached: the descriptor
+    upload is a host-to-device copy, which must not happen per call (nor inside a CUDA-graph capture)."""
+    key = (B, N, route, str(device))
+    lay = _SINGLE.get(key)
+    if lay is None:
+        b = torch.arange(B, dtype=torch.int32)
+        desc = torch.stack([b * N, torch.full_like(b, N), torch.zeros_like(b), torch.zeros_like(b)], 1)
+        lay = _SINGLE[key] = PackedLayout(B * N, [(0, B * N, route)], desc.contiguous().to(device), B, N)
+    return lay
 
 
 def split_layout(B, T, P, device):

@@ -56,40 +56,42 @@ class PatchEmbed(nn.Module):
 
 
 class _PatchProjFn(torch.autograd.Function):
-    """Patch projection as im2col (one strided copy, non-overlapping patches) + libmome's tcgen05 GEMM with
-    the bias fused; backward = wgrad GEMM + column sums (images need no gradient). Same arithmetic as the
-    Conv2d(k = s = patch) of reference vlmo.py:304 under autocast (bf16 operands, fp32 accumulation)."""
+    """Patch projection as im2col (one strided copy, non-overlapping patches) + libmome's GEMM with the bias fused;
+    backward = wgrad GEMM + column sums (images need no gradient). Same arithmetic as the Conv2d(k = s = patch) of
+    reference vlmo.py:304: bf16 operands with fp32 accumulation on the tcgen05 path (what autocast gives the conv),
+    plain fp32 on the validation path (cuDNN would use TF32 in its backward)."""
 
     @staticmethod
-    def forward(ctx, img, weight, bias, w_bf16, patch):
+    def forward(ctx, img, weight, bias, w_op, patch, code):
         B, C, H, W = img.shape
         gh, gw = H // patch, W // patch
         K = C * patch * patch
         N = weight.shape[0]
-        cols = torch.empty(B * gh * gw, K, dtype=torch.bfloat16, device=img.device)
+        cdt = torch.bfloat16 if code == L.BF16 else torch.float32
+        cols = torch.empty(B * gh * gw, K, dtype=cdt, device=img.device)
         cols.view(B, gh, gw, C, patch, patch).copy_(img.view(B, C, gh, patch, gw, patch).permute(0, 2, 4, 1, 3, 5))
         out = torch.empty(B * gh * gw, N, dtype=torch.float32, device=img.device)
-        ops.gemm(L.BF16, L.K_MAJOR, L.K_MAJOR, L.EPI_STORE, L.F32, N, K, K, N,
-                 [dict(a=cols.data_ptr(), b=w_bf16.data_ptr(), M=cols.shape[0], K=K, out=out.data_ptr(),
+        ops.gemm(code, L.K_MAJOR, L.K_MAJOR, L.EPI_STORE, L.F32, N, K, K, N,
+                 [dict(a=cols.data_ptr(), b=w_op.data_ptr(), M=cols.shape[0], K=K, out=out.data_ptr(),
                        bias=bias.data_ptr() if bias is not None else None)])
         ctx.save_for_backward(cols)
-        ctx.meta = (weight.shape, bias is not None)
+        ctx.meta = (weight.shape, bias is not None, code)
         return out.view(B, gh * gw, N)
 
     @staticmethod
     def backward(ctx, dout):
         (cols,) = ctx.saved_tensors
-        wshape, has_bias = ctx.meta
+        wshape, has_bias, code = ctx.meta
         N, K = wshape[0], cols.shape[1]
-        dy = dout.reshape(-1, N).to(torch.bfloat16)
+        dy = dout.reshape(-1, N).to(cols.dtype).contiguous()
         dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
-        ops.gemm(L.BF16, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, K, N, K, K,
+        ops.gemm(code, L.MN_MAJOR, L.MN_MAJOR, L.EPI_ATOMIC, L.F32, K, N, K, K,
                  [dict(a=dy.data_ptr(), b=cols.data_ptr(), M=N, K=dy.shape[0], out=dw.data_ptr())])
         db = None
         if has_bias:
             db = torch.zeros(N, dtype=torch.float32, device=dy.device)
             ops.colsum(dy, db)
-        return None, dw.view(wshape), db, None, None
+        return None, dw.view(wshape), db, None, None, None
 
 
 class TextEmbeddings(nn.Module):
@@ -378,15 +380,14 @@ class VLMO(nn.Module):
 
     # ---- embeddings (reference vlmo.py:298-324)
     def embed_img(self, x, img_masks, bool_masked_pos=None, img_token_type_idx=1):
+        pe = self.patch_embed.proj
         if self.precision == 'bf16':
-            pe = self.patch_embed.proj
-            w_bf16 = self._pe_cache.get('w', (pe.weight,), lambda: pe.weight.detach().reshape(pe.weight.shape[0], -1)
-                                        .to(torch.bfloat16).contiguous())
-            x = _PatchProjFn.apply(x.float().contiguous(), pe.weight, pe.bias, w_bf16, self.patch_size)
+            w_op = self._pe_cache.get('w', (pe.weight,), lambda: pe.weight.detach().reshape(pe.weight.shape[0], -1)
+                                      .to(torch.bfloat16).contiguous())
+            x = _PatchProjFn.apply(x.float().contiguous(), pe.weight, pe.bias, w_op, self.patch_size, L.BF16)
         else:
-            # fp32 validation path: keep cuDNN off TF32 so that the patch projection is true fp32
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                x = self.patch_embed(x).float()
+            w_op = pe.weight.detach().reshape(pe.weight.shape[0], -1).float().contiguous()
+            x = _PatchProjFn.apply(x.float().contiguous(), pe.weight, pe.bias, w_op, self.patch_size, L.F32)
         B, P, _ = x.shape
         if bool_masked_pos is not None:
             w = bool_masked_pos.reshape(B, P, 1).type_as(x)

@@ -266,6 +266,19 @@ typedef struct {
 int mome_block_fwd(const MomeBlockArgs* args, void* stream);
 int mome_block_bwd(const MomeBlockArgs* args, void* stream);
 
+/* ---- Optimizer step on flat buffers -------------------------------------------------------
+ * reference: apex FusedAdam / DeepSpeed Adam(adam_w_mode) built by utils/optim_factory.py:93-199 over the three-tier
+ * parameter groups of get_parameter_groups (:22-90), and the gradient clipping of train/pretrain/multimodal.py:311-330.
+ * One launch updates n consecutive fp32 parameters (a whole flat buffer or a rank's ZeRO shard of it):
+ *   g = grad * *grad_scale;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+ *   p = p (1 - lr wd) - lr (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps),   lr = lr_table[group_id[i]], wd likewise.
+ * `step` (t, >= 1) and `grad_scale` (may be NULL = 1) are DEVICE scalars. */
+int mome_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* group_id,
+                    const float* lr_table, const float* wd_table, const float* step, const float* grad_scale, float beta1,
+                    float beta2, float eps, int64_t n, void* stream);
+/* out[0] += sum_i x[i]^2 (global gradient norm for clipping) */
+int mome_sumsq(const float* x, int64_t n, float* out, void* stream);
+
 /* ---- measurement hooks (bench.py): CUDA-event timing of every mome_gemm launch on its own stream */
 int mome_prof_enable(int on);
 /* Synchronises the recorded events; returns launches, summed milliseconds and summed FLOPs. */

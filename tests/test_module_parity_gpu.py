@@ -44,12 +44,17 @@ def _expected_groups(route_log, T):
     return out
 
 
+@pytest.mark.parametrize('merge', [False, True])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('name', ['unit_full', 'unit_ragged', 'unit_vqa', 'base_c1'])
-def test_module_matches_reference_golden(name, precision):
-    """base_c1 = BASELINE configs[0] (VLMo-base 12L, batch 2, 224^2 + 40 tokens) as the unmodified reference computed it."""
+def test_module_matches_reference_golden(name, precision, merge):
+    """base_c1 = BASELINE configs[0] (VLMo-base 12L, batch 2, 224^2 + 40 tokens) as the unmodified reference computed it.
+    merge = config.train.merge_passes: False runs one backbone pass per reference infer() call (the routing log then equals
+    the reference's Block calls one for one), True (the default) packs independent sequences of several objectives into
+    shared passes (same tokens, same experts, fewer launches)."""
     gold = load_golden(name)
     cfg = case_config(gold['case'])
+    cfg.train.merge_passes = merge
     model = _build(cfg, precision)
     batch = _to_cuda(case_batch(cfg, gold['case']))
     model.transformer.route_log = []
@@ -60,10 +65,16 @@ def test_module_matches_reference_golden(name, precision):
     tol = TOL[precision]
 
     # ---- routing, bit exact: every (layer, expert, rows) assignment of the reference happens here too
-    mine = {}
+    mine, mine_rows, ref_rows = {}, {}, {}
     for (layer, route, first, rows) in model.transformer.route_log:
         mine[(layer, route, rows)] = mine.get((layer, route, rows), 0) + 1
-    assert mine == _expected_groups(gold['route_log'], cfg.model.max_text_len)
+        mine_rows[(layer, route)] = mine_rows.get((layer, route), 0) + rows
+    for (layer, route, rows, toks) in gold['route_log']:
+        ref_rows[(layer, route)] = ref_rows.get((layer, route), 0) + rows * toks
+    # every (layer, expert) processes exactly the token rows the reference routes to it ...
+    assert mine_rows == ref_rows
+    if not merge:  # ... and, pass for pass, in groups of exactly the reference's Block calls
+        assert mine == _expected_groups(gold['route_log'], cfg.model.max_text_len)
 
     # ---- losses and logits
     assert abs(float(loss) - gold['total_loss']) <= tol * abs(gold['total_loss']), (float(loss), gold['total_loss'])
@@ -203,10 +214,10 @@ def test_dedup_prefix_matches_reference_pass_structure(precision):
         loss = sum(v for k, v in out.items() if 'task_loss' in k)
         loss.backward()
         res.append((out, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
-                    len(model.transformer.route_log)))
+                    sum(rows for (_, _, _, rows) in model.transformer.route_log)))
     (o0, g0, n0), (o1, g1, n1) = res
     tol = 1e-5 if precision == 'fp32' else 2e-3
-    assert n1 < n0  # fewer expert-group executions
+    assert n1 < n0  # fewer token rows through the pre-fusion layers
     for k in ('mlm_task_loss', 'itc_task_loss', 'itm_task_loss'):
         assert abs(float(o0[k]) - float(o1[k])) <= tol * abs(float(o0[k])), k
     assert torch.equal(o0['itm_neg_img'], o1['itm_neg_img']) and torch.equal(o0['itm_neg_txt'], o1['itm_neg_txt'])
