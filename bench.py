@@ -61,6 +61,10 @@ def parse():
     ap.add_argument('--dropout', default='shipped', choices=['shipped', 'off'],
                     help="'shipped': drop_rate / attn_drop_rate / drop_path_rate = 0.1 as in the reference's conf/model/vlmo_base.yaml; "
                          "'off': the parity configuration")
+    ap.add_argument('--optimizer', default='flat', choices=['flat', 'torch'],
+                    help="'flat': exploremultimodal_b200.optim.FlatAdamW (one mome_adamw_flat launch per flat buffer, gradient clipping "
+                         "at 5.0 fused, the reference's three-tier parameter groups); 'torch': torch.optim.AdamW(fused=True)")
+    ap.add_argument('--zero2', action='store_true', help='ZeRO-2 style: reduce-scatter gradients, shard Adam state, all-gather parameters (N > 1)')
     ap.add_argument('--reduce-dtype', default='fp32', choices=['fp32', 'bf16'], help='dtype of the gradient all-reduce (N > 1)')
     ap.add_argument('--dedup', action='store_true',
                     help='opt-in cross-pass de-duplication of the pre-fusion layers (config.train.dedup_prefix, SURVEY.md 8(f) N3): '
@@ -298,6 +302,17 @@ def grad_sync_check(sync, world, dev):
     return {'identical_across_ranks': bool(same), 'buffers': len(flats), 'abs_sum': float(sums[len(flats):].sum())}
 
 
+def param_sync_check(sync, world):
+    """ZeRO-2: after the all-gather every rank must hold bit-identical parameters."""
+    import torch
+    import torch.distributed as dist
+    flats = [fp for (_, fp, _) in sync.flat_sets() if fp is not None]
+    sums = torch.stack([f.double().sum() for f in flats] + [f.double().abs().sum() for f in flats])
+    gathered = [torch.empty_like(sums) for _ in range(world)]
+    dist.all_gather(gathered, sums)
+    return {'identical_across_ranks': bool(all(torch.equal(gathered[0], g) for g in gathered[1:])), 'buffers': len(flats)}
+
+
 def block_route_tflops(model, cfg, B, dev, iters=10):
     """BASELINE metric (ii): one reference-API `Block.forward(x, mask, route)` + backward per route at the step's shapes
     (B sequences of 197 / 40 / 237 tokens at 224^2), CUDA events, TFLOP/s = 3 x (N 24 d^2 + 4 N^2 d) x B / time."""
@@ -375,8 +390,6 @@ def run_mome(args):
         with torch.no_grad():
             for p in model.parameters():
                 dist.broadcast(p, 0)  # in-place on the Parameter itself: bumps its version, refreshing the bf16 copies
-    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.05, fused=True,
-                            capturable=not args.no_graph and not args.ncu_step)
 
     B = args.batch
     host = make_batch(cfg, B, seed=1234, rank=rank, lengths=args.lengths, pin_memory=True, vqa=vqa)
@@ -391,7 +404,21 @@ def run_mome(args):
     loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
 
     from exploremultimodal_b200.ddp import GradSync
-    sync = GradSync(model, world, reduce_dtype=args.reduce_dtype)  # flat per-block gradient buffers, reduced as blocks finish
+    from exploremultimodal_b200.optim import FlatAdamW, get_parameter_groups
+    zero2 = args.zero2 and world > 1 and args.optimizer == 'flat'
+    # flat per-block gradient (and parameter) buffers, reduced / reduce-scattered as blocks finish their backward
+    sync = GradSync(model, world, reduce_dtype=args.reduce_dtype, reduce='reduce_scatter' if zero2 else 'all_reduce',
+                    flatten_params=args.optimizer == 'flat')
+    if args.optimizer == 'flat':
+        # hyper-parameters of the reference's pretraining recipe (conf/train/pretrain_mum.yaml: AdamW betas (0.9, 0.98), eps 1e-6,
+        # weight decay 0.05, clip_grad 5.0; lr multipliers 1) over get_parameter_groups' three tiers
+        groups = get_parameter_groups(model, base_lr=1e-4, lr_mult_head=1.0, lr_mult_fusion=1.0, weight_decay=0.05,
+                                      skip_list=model.no_weight_decay())
+        opt = FlatAdamW(sync, groups, betas=(0.9, 0.98), eps=1e-6, clip_grad=5.0, zero2=zero2)
+        opt.on_step = model.invalidate_weight_cache
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.05, fused=True,
+                                capturable=not args.no_graph and not args.ncu_step)
 
     def step_body():
         opt.zero_grad(set_to_none=False)
@@ -420,7 +447,7 @@ def run_mome(args):
     with torch.cuda.stream(side):
         for _ in range(n_warm):
             step_body()
-        if world > 1:
+        if world > 1 and not zero2:
             checks['grad_sync'] = grad_sync_check(sync, world, dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -432,8 +459,11 @@ def run_mome(args):
         eager_ms_step = e0.elapsed_time(e1) / 2
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1 and not zero2:
         assert checks['grad_sync']['identical_across_ranks'], 'ranks hold different gradients after GradSync.finish()'
+    if zero2:
+        checks['param_sync'] = param_sync_check(sync, world)
+        assert checks['param_sync']['identical_across_ranks'], 'ranks hold different parameters after the sharded optimizer step'
     if args.ncu_step:
         torch.cuda.profiler.start()
         step_body()
@@ -564,6 +594,10 @@ def run_mome(args):
         config['itc_parity'] = checks.get('itc_parity')
         config['grad_sync'] = checks.get('grad_sync')
         config['grad_reduce_dtype'] = args.reduce_dtype
+        config['param_sync'] = checks.get('param_sync')
+    config['optimizer'] = ('FlatAdamW (mome_adamw_flat, clip 5.0 fused' + (', ZeRO-2 sharded state' if zero2 else '') + ')') if args.optimizer == 'flat' else 'torch.optim.AdamW(fused)'
+    if world > 1:
+        pass
     line = {
         'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': n_warm,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -208,7 +208,8 @@ def test_gradsync_flat_buffers_back_every_gradient():
     sync = GradSync(model, 1)
     assert len(sync.block_flat) == len(model.transformer.blocks)
     total = sum(f.numel() for f in sync.block_flat) + sync.rest_flat.numel()
-    assert total == sum(p.numel() for p in model.parameters() if p.requires_grad)
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert n_train <= total < n_train + 4 * (len(sync.block_flat) + 1)   # each buffer is padded to a multiple of 4 * world elements
     for blk, flat in zip(model.transformer.blocks, sync.block_flat):
         assert blk.fused_grad_accumulation and blk.grads_ready_hook is None
         lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
@@ -238,3 +239,30 @@ def test_mlm_compaction_is_ordered_and_counts_overflow():
         assert bool((tgt[n:] == -100).all()) and int(overflow) == max(0, 37 - cap)
     order, tgt, overflow = compact_masked_rows(torch.full((16,), -100), 8)
     assert bool((tgt == -100).all()) and int(overflow) == 0
+
+
+def test_parameter_groups_follow_the_reference_name_rules():
+    """optim.get_parameter_groups: tiers and weight decay by parameter NAME (reference utils/optim_factory.py:22-90)."""
+    from exploremultimodal_b200 import build_model, make_config
+    from exploremultimodal_b200.optim import get_parameter_groups
+    model = build_model(make_config('vlmo_unit'))   # depth 4, fusion_layer 2
+    groups = get_parameter_groups(model, base_lr=1.0, lr_mult_head=5.0, lr_mult_fusion=2.0, weight_decay=0.05,
+                                  skip_list=model.no_weight_decay())
+    where = {n: g for g in groups for n in g['names']}
+    expect = {
+        'transformer.blocks.3.mlp.vl.fc1.weight': ('fusion_layer_decay', 2.0, 0.05),
+        'transformer.blocks.2.attn.q_bias': ('fusion_layer_no_decay', 2.0, 0.0),
+        'transformer.blocks.1.attn.qkv.weight': ('bottom_layer_decay', 1.0, 0.05),
+        'transformer.blocks.0.gamma_1': ('bottom_layer_no_decay', 1.0, 0.0),
+        'transformer.pooler.dense.weight': ('fusion_layer_decay', 2.0, 0.05),
+        'itc_head.dense.v.weight': ('head_layer_decay', 5.0, 0.05),
+        'mlm_head.bias': ('head_layer_no_decay', 5.0, 0.0),
+        'itc_temp': ('bottom_layer_no_decay', 1.0, 0.0),
+        'transformer.pos_embed': ('bottom_layer_no_decay', 1.0, 0.0),
+        'transformer.txt_embeddings.word_embeddings.weight': ('bottom_layer_decay', 1.0, 0.05),
+    }
+    for name, (gname, lr, wd) in expect.items():
+        g = where[name]
+        assert (g['name'], g['lr'], g['weight_decay']) == (gname, lr, wd), name
+    n_train = sum(1 for _, p in model.named_parameters() if p.requires_grad)
+    assert sum(len(g['params']) for g in groups) == n_train
