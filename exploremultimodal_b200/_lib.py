@@ -88,6 +88,8 @@ _SIGNATURES = {
     'mome_itc_fwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'mome_itc_bwd_peer': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mome_itc_gather_peer': (C.c_int, [_P, _I, _I, _I, _P, _P, _P]),
+    'mome_ce_fwd': (C.c_int, [_P, _L, _I, _I, _P, _L, _P, _P, _P, _P, _P]),
+    'mome_ce_bwd': (C.c_int, [_P, _L, _I, _I, _P, _L, _P, _P, _P]),
     'mome_adamw_flat': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _L, _P]),
     'mome_sumsq': (C.c_int, [_P, _L, _P, _P]),
     'mome_block_fwd': (C.c_int, [C.POINTER(BlockArgs), _P]),

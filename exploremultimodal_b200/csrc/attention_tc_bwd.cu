@@ -10,7 +10,7 @@
 // two dQ_i accumulate over the whole item. Per block:
 //
 //   tcgen05    S  = Q_i K_j^T, dP = dO_i V_j^T                         (SS, K-major)        -> TMEM S, dP (128 columns each)
-//   8 warps    thread = (query row, half of the block's keys): P = exp2(S scale log2e - lse), dropout,
+//   8 / 16 warps  thread = (query row, half / quarter of the block's keys): P = exp2(S scale log2e - lse), dropout,
 //              dS = P o (dP - delta); bf16 P and dS -> two SWIZZLE_128B smem tiles [128 q][128 keys]
 //   tcgen05    dV_j += P^T dO_i, dK_j += dS^T Q_i   (A = the smem tile read MN-major: the transposition is free)
 //              dQ_i += dS K_j                        (A = the same dS tile read K-major)      -> TMEM accumulators
@@ -21,7 +21,7 @@
 //
 //   warp 0      producer (TMA; cp.async gather for layouts whose second range is not 8-row aligned)
 //   warp 1      one elected thread issues every tcgen05.mma
-//   warps 2-9   P / dS group, also drains the accumulators (x scale) into dqkv
+//   warps 2-9 (2-17)  P / dS group (8 or 16 warps), also drains the accumulators (x scale) into dqkv
 //
 // Replaces: the autograd backward of reference vlmo.py:79-95.
 #include <cuda.h>
@@ -51,7 +51,7 @@ constexpr int kPOff = 131072, kSOff = 163840;                            // P, d
 constexpr int kMetaOff = 196608;                                          // keep words [8], seq desc [4]
 constexpr int kBarOff = kMetaOff + 64;
 constexpr int kBwdSmem = kBarOff + 128 + 1024;
-constexpr int kBwdThreads = 64 + 256;
+constexpr int kBwdThreads8 = 64 + 256, kBwdThreads16 = 64 + 512;  // producer + MMA warps + 8 or 16 P / dS warps
 constexpr uint32_t kColDQ = 0, kColDK = 128, kColDV = 192, kColS = 256, kColDP = 384;
 
 struct Seq {
@@ -139,10 +139,25 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   }
 }
 
-// EARLY_S (experimental, MOME_ATTN_TC_BWD=2): S / dP of the next block of the item are issued before the accumulate
-// MMAs of the current one, so the P / dS group works on block b + 1 while the tensor core finishes block b.
-template <bool DROP, bool EARLY_S>
-__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
+// GW = warps of the P / dS group: 8 (a thread owns a query row x 64 keys of the block) or 16 (x 32 keys). The P / dS
+// phase is a serial per-thread chain of exponentials between two tensor-core phases; with 16 warps it is half as long
+// and each scheduler has four warps to interleave (MOME_ATTN_TC_BWD=1 selects 8, the default 3 selects 16).
+// EARLY_S (experimental, MOME_ATTN_TC_BWD=2, 8 warps): S / dP of the next block of the item are issued before the
+// accumulate MMAs of the current one (measured: no gain, 412 vs 405 us).
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x16(taddr, r); }
+
+template <bool DROP, bool EARLY_S, int GW>
+__global__ void __launch_bounds__(64 + 32 * GW, 1) attn_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
+  constexpr int kBwdThreads = 64 + 32 * GW;
+  constexpr int kParts = GW / 4;        // key parts of a block = column parts of the 64-wide accumulators
+  constexpr int KP = kTile / kParts;    // keys of the block per thread
+  constexpr int DC = kHd / kParts;      // accumulator columns per thread in the drains
+  constexpr int kGroupThreads = 32 * GW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -166,12 +181,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     mbar_init(full, 2);
     mbar_init(empty, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, kGroupThreads);
     mbar_init(pds_free, 1);
     mbar_init(dkv_full, 1);
-    mbar_init(dkv_free, 256);
+    mbar_init(dkv_free, kGroupThreads);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 256);
+    mbar_init(dq_free, kGroupThreads);
     fence_barrier_init();
     tma_prefetch_desc(&p.qkv32);
     tma_prefetch_desc(&p.qkv8);
@@ -321,15 +336,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     }
   } else {
     // ------------------------------------------------------------------------------------ P / dS group
-    const int wi = warp - 2, half = wi >> 2, quarter = warp & 3;
+    const int wi = warp - 2, part = wi >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const float sl2 = p.scale * kLog2e;
     const uint32_t dkey = DROP ? drop_mix(p.drop_salt, __ldg(p.drop_seed)) : 0u;
     const float dscale = drop_scale(p.drop_thr);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     // this thread's 128-byte segment of the P / dS tiles (64 keys), as shared-space addresses (st.shared, not generic st)
-    const uint32_t prow = smem_u32(smem + kPOff + half * 16384 + row * 128);
-    const uint32_t srow = smem_u32(smem + kSOff + half * 16384 + row * 128);
+    const uint32_t prow = smem_u32(smem + kPOff + ((part * KP) >> 6) * 16384 + row * 128);
+    const uint32_t srow = smem_u32(smem + kSOff + ((part * KP) >> 6) * 16384 + row * 128);
+    const int cb = ((part * KP) & 63) >> 3;  // first 16-byte chunk of this thread's keys inside the 128-byte row segment
     const int sw = row & 7;
     const long long ld3 = 3LL * d;
     uint32_t blk = 0, jcount = 0;
@@ -351,23 +367,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         Dr[i] = q < n ? __ldg(p.delta + stat0 + q) : 0.f;
       }
       for (int j = 0; j < nt; ++j) {
-        // keep bits of this thread's 64 keys: keys j 128 + half 64 + [0, 64)
-        const uint32_t kw_lo = meta[j * 4 + half * 2], kw_hi = meta[j * 4 + half * 2 + 1];
+        // keep bits of this thread's KP keys: keys j 128 + part KP + [0, KP)
+        const uint32_t kw_lo = meta[j * 4 + ((part * KP) >> 5)], kw_hi = KP > 32 ? meta[j * 4 + ((part * KP) >> 5) + 1] : 0u;
         for (int i = 0; i < nt; ++i, ++blk) {
           const int q = i * kTile + row;
           const float L = Lr[i], D = Dr[i];
-          const uint32_t drow = attn_drop_row(s, H, h, p.max_seq_len, q) + ((j * kTile + half * 64) >> 1);
+          const uint32_t drow = attn_drop_row(s, H, h, p.max_seq_len, q) + ((j * kTile + part * KP) >> 1);
           mbar_wait_park(sdp_full, blk & 1);
           if (!EARLY_S && blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // the previous block's MMAs are done with the P / dS tiles
           __syncwarp();
           tcgen05_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {  // 16 keys at a time
+          for (int c = 0; c < KP / 16; ++c) {  // 16 keys at a time
             uint32_t sv[16], dv[16];
-            tmem_ld_32x16(trow + kColS + half * 64 + c * 16, sv);
-            tmem_ld_32x16(trow + kColDP + half * 64 + c * 16, dv);
+            tmem_ld_32x16(trow + kColS + part * KP + c * 16, sv);
+            tmem_ld_32x16(trow + kColDP + part * KP + c * 16, dv);
             tmem_ld_wait();
-            const uint32_t kw = ((c < 2 ? kw_lo : kw_hi) >> (16 * (c & 1))) & 0xffffu;
+            const uint32_t kw = ((c < 2 ? kw_lo : kw_hi) >> (16 * (c & 1))) & 0xffffu;  // KP = 32: one word, c in {0, 1}
             uint32_t pp[8], ds[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -390,11 +406,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
               ds[e] = pack_bf16(s0, s1);
             }
             if (EARLY_S && c == 0 && blk > 0) mbar_wait_park(pds_free, (blk & 1) ^ 1);  // first store of the block
-            // keys c 16 + [0, 16) of this thread's 64: 16-byte chunks 2 c and 2 c + 1 of the row segment
-            sts_v4_u32(prow + (((2 * c) ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
-            sts_v4_u32(prow + (((2 * c + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
-            sts_v4_u32(srow + (((2 * c) ^ sw) << 4), ds[0], ds[1], ds[2], ds[3]);
-            sts_v4_u32(srow + (((2 * c + 1) ^ sw) << 4), ds[4], ds[5], ds[6], ds[7]);
+            // keys c 16 + [0, 16) of this thread's KP: 16-byte chunks cb + 2 c and cb + 2 c + 1 of the row segment
+            sts_v4_u32(prow + (((cb + 2 * c) ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
+            sts_v4_u32(prow + (((cb + 2 * c + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
+            sts_v4_u32(srow + (((cb + 2 * c) ^ sw) << 4), ds[0], ds[1], ds[2], ds[3]);
+            sts_v4_u32(srow + (((cb + 2 * c + 1) ^ sw) << 4), ds[4], ds[5], ds[6], ds[7]);
           }
           fence_proxy_async();  // the tiles are read by the tensor core (async proxy)
           tcgen05_fence_before();
@@ -406,19 +422,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         __syncwarp();
         tcgen05_fence_after();
         {
-          uint32_t a[32], b[32];
-          tmem_ld_32x32(trow + kColDK + half * 32, a);
-          tmem_ld_32x32(trow + kColDV + half * 32, b);
+          uint32_t a[DC], b[DC];
+          tmem_ld_cols<DC>(trow + kColDK + part * DC, a);
+          tmem_ld_cols<DC>(trow + kColDV + part * DC, b);
           tmem_ld_wait();
           tcgen05_fence_before();
           mbar_arrive(dkv_free);
           const int key = j * kTile + row;
           if (key < n) {
-            __nv_bfloat16* base = p.dqkv + seq_row(sd, key) * ld3 + h * kHd + half * 32;
+            __nv_bfloat16* base = p.dqkv + seq_row(sd, key) * ld3 + h * kHd + part * DC;
             uint4* dk = reinterpret_cast<uint4*>(base + d);
             uint4* dvp = reinterpret_cast<uint4*>(base + 2 * d);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < DC / 8; ++e) {
               dk[e] = make_uint4(pack_bf16(__uint_as_float(a[8 * e]) * p.scale, __uint_as_float(a[8 * e + 1]) * p.scale),
                                  pack_bf16(__uint_as_float(a[8 * e + 2]) * p.scale, __uint_as_float(a[8 * e + 3]) * p.scale),
                                  pack_bf16(__uint_as_float(a[8 * e + 4]) * p.scale, __uint_as_float(a[8 * e + 5]) * p.scale),
@@ -436,9 +452,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       __syncwarp();
       tcgen05_fence_after();
       {
-        uint32_t a[32], b[32];
-        tmem_ld_32x32(trow + kColDQ + half * 32, a);
-        if (nt > 1) tmem_ld_32x32(trow + kColDQ + 64 + half * 32, b);
+        uint32_t a[DC], b[DC];
+        tmem_ld_cols<DC>(trow + kColDQ + part * DC, a);
+        if (nt > 1) tmem_ld_cols<DC>(trow + kColDQ + 64 + part * DC, b);
         tmem_ld_wait();
         tcgen05_fence_before();
         mbar_arrive(dq_free);
@@ -446,10 +462,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         for (int i = 0; i < 2; ++i) {
           const int q = i * kTile + row;
           if (i < nt && q < n) {
-            uint4* dq = reinterpret_cast<uint4*>(p.dqkv + seq_row(sd, q) * ld3 + h * kHd + half * 32);
+            uint4* dq = reinterpret_cast<uint4*>(p.dqkv + seq_row(sd, q) * ld3 + h * kHd + part * DC);
             const uint32_t* v = i == 0 ? a : b;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < DC / 8; ++e)
               dq[e] = make_uint4(pack_bf16(__uint_as_float(v[8 * e]) * p.scale, __uint_as_float(v[8 * e + 1]) * p.scale),
                                  pack_bf16(__uint_as_float(v[8 * e + 2]) * p.scale, __uint_as_float(v[8 * e + 3]) * p.scale),
                                  pack_bf16(__uint_as_float(v[8 * e + 4]) * p.scale, __uint_as_float(v[8 * e + 5]) * p.scale),
@@ -482,15 +498,18 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   MOME_REQUIRE(max_seq_len <= kMaxKeys, "attn_bwd_tc: max_seq_len %d > %d", max_seq_len, kMaxKeys);
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in(attn_bwd_tc_kernel<false, false>, kBwdSmem, "attn_bwd_tc");
-    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, false>, kBwdSmem, "attn_bwd_tc");
-    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<false, true>, kBwdSmem, "attn_bwd_tc");
-    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, true>, kBwdSmem, "attn_bwd_tc");
+    int rc = opt_in(attn_bwd_tc_kernel<false, false, 8>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, false, 8>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<false, true, 8>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, true, 8>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<false, false, 16>, kBwdSmem, "attn_bwd_tc");
+    if (rc == MOME_OK) rc = opt_in(attn_bwd_tc_kernel<true, false, 16>, kBwdSmem, "attn_bwd_tc");
     if (rc != MOME_OK) return rc;
     configured = true;
   }
   const char* variant = getenv("MOME_ATTN_TC_BWD");
   const bool early_s = variant != nullptr && variant[0] == '2';
+  const bool wide = variant == nullptr || variant[0] == '3';  // 16 P / dS warps; "1" / "2" keep 8
   BwdParams p;
   const int64_t d = static_cast<int64_t>(H) * kHd, d3 = 3 * d;
   int rc = tma_encode_bf16_2d(&p.qkv32, qkv, d3, tokens, d3, kHd, 32);
@@ -519,10 +538,12 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   if (rc != MOME_OK) return rc;
   const int grid = std::min(p.num_items, sm_count());
   const bool drop = drop_seed != nullptr && drop_p > 0.f;
-  if (drop && early_s) attn_bwd_tc_kernel<true, true><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
-  else if (drop) attn_bwd_tc_kernel<true, false><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
-  else if (early_s) attn_bwd_tc_kernel<false, true><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
-  else attn_bwd_tc_kernel<false, false><<<grid, kBwdThreads, kBwdSmem, stream>>>(p);
+  if (wide && drop) attn_bwd_tc_kernel<true, false, 16><<<grid, kBwdThreads16, kBwdSmem, stream>>>(p);
+  else if (wide) attn_bwd_tc_kernel<false, false, 16><<<grid, kBwdThreads16, kBwdSmem, stream>>>(p);
+  else if (drop && early_s) attn_bwd_tc_kernel<true, true, 8><<<grid, kBwdThreads8, kBwdSmem, stream>>>(p);
+  else if (drop) attn_bwd_tc_kernel<true, false, 8><<<grid, kBwdThreads8, kBwdSmem, stream>>>(p);
+  else if (early_s) attn_bwd_tc_kernel<false, true, 8><<<grid, kBwdThreads8, kBwdSmem, stream>>>(p);
+  else attn_bwd_tc_kernel<false, false, 8><<<grid, kBwdThreads8, kBwdSmem, stream>>>(p);
   return check_launch("attn_bwd_tc");
 }
 

@@ -51,7 +51,21 @@ def mlm_from_feats(model, txt_feats, labels, txt_ids):
     K = B * T if B * T <= 256 else min(B * T, max(256, int(cap * B * T)))
     order, tgt, overflow = compact_masked_rows(flat, K)
     rows = txt_feats.reshape(B * T, d)[order]
-    with model.transformer._autocast():
+    tr = model.transformer
+    if tr.precision == 'bf16' and getattr(model.config.train, 'fused_mlm_head', True) and d % 64 == 0:
+        # decoder GEMM (tcgen05) + cross-entropy + accuracy with the [K, vocab] logits kept once, in bf16, and turned into
+        # their own gradient in place (heads._DecoderCE). `mlm_logits` is not returned on this path (nothing in the
+        # reference's loop reads it, train/pretrain/multimodal.py:336-391); config.train.fused_mlm_head = False restores it.
+        w = model.mlm_head.decoder.weight
+        w_bf16 = tr._pe_cache.get('mlm_decoder', (w,), lambda: w.detach().to(torch.bfloat16).contiguous())
+        with tr._autocast():
+            loss_sum, cnt = model.mlm_head.fused_loss(rows, tgt, w_bf16)
+        count = cnt[0].to(torch.int64)
+        loss = loss_sum / count.clamp(min=1).float()
+        acc = cnt[1].float() / count.clamp(min=1).float()
+        return {'mlm_task_loss': loss, 'mlm_labels': tgt, 'mlm_ids': txt_ids, 'mlm_mean_acc': acc, 'mlm_count': count,
+                'mlm_overflow': overflow}
+    with tr._autocast():
         logits = model.mlm_head(rows)
     acc, count = compute_accuracy(logits, tgt)
     loss = F.cross_entropy(logits.float().view(-1, model.config.model.vocab_size), tgt.view(-1), ignore_index=-100,

@@ -266,6 +266,17 @@ typedef struct {
 int mome_block_fwd(const MomeBlockArgs* args, void* stream);
 int mome_block_bwd(const MomeBlockArgs* args, void* stream);
 
+/* ---- MLM head tail: softmax cross-entropy over the vocabulary on bf16 logits ----------------
+ * reference: F.cross_entropy(mlm_logits, mlm_labels, ignore_index=-100) + compute_accuracy, objectives.py:52-66, 24-37.
+ * logits: bf16 [rows, ld], columns [cols, ld) are padding (ld % 8 == 0). mome_ce_fwd writes lse[row] for every row and
+ * ACCUMULATES loss_sum (sum over valid rows of lse - logit[target]), count (valid rows) and correct (argmax == target);
+ * mome_ce_bwd overwrites logits IN PLACE with d loss_sum / d logits * *gscale (0 for ignored rows and padding), so the
+ * [rows, vocab] matrix exists once, in bf16; gscale is a DEVICE scalar (upstream gradient / count). */
+int mome_ce_fwd(const void* logits, int64_t ld, int32_t rows, int32_t cols, const int64_t* targets, int64_t ignore_index,
+                float* lse, float* loss_sum, int32_t* count, int32_t* correct, void* stream);
+int mome_ce_bwd(void* logits, int64_t ld, int32_t rows, int32_t cols, const int64_t* targets, int64_t ignore_index,
+                const float* lse, const float* gscale, void* stream);
+
 /* ---- Optimizer step on flat buffers -------------------------------------------------------
  * reference: apex FusedAdam / DeepSpeed Adam(adam_w_mode) built by utils/optim_factory.py:93-199 over the three-tier
  * parameter groups of get_parameter_groups (:22-90), and the gradient clipping of train/pretrain/multimodal.py:311-330.
