@@ -54,6 +54,9 @@ class GradSync:
             blk._pending_bwd = 0
             self.blocks.append((blk, ps))
             self.block_flat.append(flat)
+        te = getattr(model.transformer, 'txt_embeddings', None)
+        if te is not None:
+            te.fused_grad_accumulation = True   # embedding-table gradients are scattered straight into the flat buffer
         self.rest = [p for p in model.parameters() if p.requires_grad and id(p) not in in_block]
         self.rest_flat = self._flatten(self.rest)
 

@@ -112,6 +112,61 @@ class TextEmbeddings(nn.Module):
         return self.dropout(self.LayerNorm(e))
 
 
+class _TextEmbedFn(torch.autograd.Function):
+    """`embed_txt` (reference vlmo.py:321-324 over transformers BertEmbeddings) as one libmome kernel per direction:
+    word + position + token_type(0) -> LayerNorm -> dropout -> + modality-type(0); backward = LayerNorm backward + red.add
+    scatters into the embedding tables (torch's embedding backward sorts the indices: ~12 launches per table)."""
+
+    @staticmethod
+    def forward(ctx, ids, word, pos, type_w, ln_w, ln_b, modal_w, eps, drop, holder):
+        B, T = ids.shape
+        d = word.shape[1]
+        rows = B * T
+        dev = word.device
+        ids = ids.contiguous()
+        y = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        xhat = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        seed, salt, p = drop if drop else (None, 0, 0.0)
+        L.check(L.lib().mome_text_embed_fwd(ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type_w.data_ptr(), ln_w.data_ptr(),
+                                            ln_b.data_ptr(), modal_w.data_ptr(), y.data_ptr(), xhat.data_ptr(), rstd.data_ptr(),
+                                            rows, T, d, eps, seed.data_ptr() if seed is not None else None, salt, p, L.stream()),
+                'mome_text_embed_fwd')
+        ctx.save_for_backward(ids, xhat, rstd, ln_w)
+        ctx.meta = (B, T, d, word.shape, pos.shape, type_w.shape, modal_w.shape, drop, holder)
+        ctx.params = (word, pos)
+        return y.view(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, xhat, rstd, ln_w = ctx.saved_tensors
+        B, T, d, wshape, pshape, tshape, mshape, drop, holder = ctx.meta
+        dev = dy.device
+        dy = dy.reshape(B * T, d).float().contiguous()
+        word, pos = ctx.params
+        f32 = dict(dtype=torch.float32, device=dev)
+        # the two tables receive scattered rows: add straight into existing fp32 .grad buffers when the owner allows it
+        # (GradSync's flat buffers), else into fresh zeroed tensors that autograd accumulates
+        fused = getattr(holder, 'fused_grad_accumulation', False)
+
+        def target(p, shape):
+            if fused and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous():
+                return p.grad, None
+            t = torch.zeros(shape, **f32)
+            return t, t
+        dword, ret_word = target(word, wshape)
+        dpos, ret_pos = target(pos, pshape)
+        dtype_w, dmodal_w = torch.zeros(tshape, **f32), torch.zeros(mshape, **f32)
+        dln_w, dln_b = torch.zeros(d, **f32), torch.zeros(d, **f32)
+        ws = torch.empty(int(L.lib().mome_text_embed_ws_bytes(d)), dtype=torch.uint8, device=dev)
+        seed, salt, p = drop if drop else (None, 0, 0.0)
+        L.check(L.lib().mome_text_embed_bwd(dy.data_ptr(), ids.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), ln_w.data_ptr(),
+                                            dword.data_ptr(), dpos.data_ptr(), dtype_w.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
+                                            dmodal_w.data_ptr(), B * T, T, d, seed.data_ptr() if seed is not None else None, salt, p,
+                                            ws.data_ptr(), ws.numel(), L.stream()), 'mome_text_embed_bwd')
+        return None, ret_word, ret_pos, dtype_w, dln_w, dln_b, dmodal_w, None, None, None
+
+
 class Pooler(nn.Module):
     """tanh(dense(x[:, 0])) (transformers BertPooler, reference vlmo.py:290)."""
 
@@ -338,6 +393,7 @@ class VLMO(nn.Module):
         self._drop_state = None
         for i, b in enumerate(self.blocks):
             b.layer_index = i
+        self.fused_text_embedding = True  # embed_txt as one libmome kernel per direction (False: stock PyTorch modules)
         self.route_log = None  # set to a list to record (layer, route, first_row, rows) per expert group
 
     def _init_weights(self, m):
@@ -397,6 +453,20 @@ class VLMO(nn.Module):
         return x + self.token_type_embeddings(torch.full_like(img_masks, img_token_type_idx))
 
     def embed_txt(self, txt, txt_masks):
+        te = self.txt_embeddings
+        d = te.word_embeddings.weight.shape[1]
+        if self.fused_text_embedding and d % 4 == 0 and d <= 1024 and txt.shape[1] <= te.position_embeddings.weight.shape[0]:
+            drop = None
+            if self.training and te.dropout.p > 0:
+                if self.precision != 'bf16':
+                    raise NotImplementedError('dropout / stochastic depth are implemented on the bf16 path only')
+                if self._drop_state is None:
+                    self.advance_dropout()
+                self._drop_state['calls'] += 1
+                drop = (self._drop_state['seed'], (0x7e000000 + self._drop_state['calls'] * 4096) & 0x7fffffff, float(te.dropout.p))
+            return _TextEmbedFn.apply(txt, te.word_embeddings.weight, te.position_embeddings.weight, te.token_type_embeddings.weight,
+                                      te.LayerNorm.weight, te.LayerNorm.bias, self.token_type_embeddings.weight, te.LayerNorm.eps,
+                                      drop, te)
         return self.txt_embeddings(input_ids=txt) + self.token_type_embeddings(torch.zeros_like(txt_masks))
 
     # ---- packed execution

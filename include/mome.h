@@ -277,6 +277,20 @@ int mome_ce_fwd(const void* logits, int64_t ld, int32_t rows, int32_t cols, cons
 int mome_ce_bwd(void* logits, int64_t ld, int32_t rows, int32_t cols, const int64_t* targets, int64_t ignore_index,
                 const float* lse, const float* gscale, void* stream);
 
+/* ---- Text input embedding ---------------------------------------------------------------------
+ * reference: transformers BertEmbeddings as used at vlmo.py:259 (word + position + token_type(0) -> LayerNorm(eps 1e-12)
+ * -> dropout) plus `+ token_type_embeddings(zeros)` of embed_txt, vlmo.py:321-324. rows = B * T tokens in row-major (b, t)
+ * order; all tables fp32. y [rows, d] fp32; xhat [rows, d] and rstd [rows] are saved for the backward. The backward
+ * ACCUMULATES into dword [vocab, d], dpos [T.., d] (red.add scatter) and dtype0 / dln_w / dln_b / dmodal0 [d] (may be NULL). */
+int mome_text_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* ln_w,
+                        const float* ln_b, const float* modal0, float* y, float* xhat, float* rstd, int64_t rows, int32_t T,
+                        int32_t d, float eps, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream);
+size_t mome_text_embed_ws_bytes(int32_t d);
+int mome_text_embed_bwd(const float* dy, const int64_t* ids, const float* xhat, const float* rstd, const float* ln_w,
+                        float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b, float* dmodal0, int64_t rows,
+                        int32_t T, int32_t d, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* ---- Optimizer step on flat buffers -------------------------------------------------------
  * reference: apex FusedAdam / DeepSpeed Adam(adam_w_mode) built by utils/optim_factory.py:93-199 over the three-tier
  * parameter groups of get_parameter_groups (:22-90), and the gradient clipping of train/pretrain/multimodal.py:311-330.

@@ -488,3 +488,35 @@ def test_ce_fwd_bwd_matches_torch():
         L.check(L.lib().mome_ce_bwd(lb.data_ptr(), ld, rows, cols, tg.data_ptr(), -100, lse.data_ptr(), gs.data_ptr(), L.stream()), 'ce_bwd')
         assert rel_err(lb[:, :cols].float().cpu(), 0.37 * ref_in.grad) < 6e-3      # bf16 storage of the gradient
         assert float(lb[:, cols:].float().abs().max()) == 0.0 if ld > cols else True
+
+
+def test_text_embedding_kernel_matches_modules():
+    """VLMO.embed_txt through mome_text_embed_fwd / _bwd against the stock modules (BertEmbeddings layout + token-type add)."""
+    from exploremultimodal_b200 import build_model, make_config
+    from exploremultimodal_b200.synthetic import make_batch, synth_state_dict
+    cfg = make_config('vlmo_unit', parity=True)
+    cfg.model.precision = 'fp32'
+    model = build_model(cfg)
+    shapes = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(synth_state_dict(shapes, cfg.model.init_values))
+    model.cuda().train()
+    T = model.transformer
+    batch = make_batch(cfg, 6, seed=4, lengths='realistic')
+    ids, mask = batch['text_ids'].cuda(), batch['text_mask'].cuda()
+    g = torch.randn(6, cfg.model.max_text_len, cfg.model.embed_dim, generator=torch.Generator().manual_seed(1)).cuda()
+    res = []
+    names = ['txt_embeddings.word_embeddings.weight', 'txt_embeddings.position_embeddings.weight',
+             'txt_embeddings.token_type_embeddings.weight', 'txt_embeddings.LayerNorm.weight', 'txt_embeddings.LayerNorm.bias',
+             'token_type_embeddings.weight']
+    params = dict(T.named_parameters())
+    for fused in (False, True):
+        T.fused_text_embedding = fused
+        for n in names:
+            params[n].grad = None
+        y = T.embed_txt(ids, mask)
+        y.backward(g)
+        res.append((y.detach().clone(), {n: params[n].grad.clone() for n in names}))
+    (y0, g0), (y1, g1) = res
+    assert rel_err(y1, y0) < 1e-6
+    for n in names:
+        assert rel_err(g1[n], g0[n]) < 1e-5, n
