@@ -306,7 +306,7 @@ def param_sync_check(sync, world):
     """ZeRO-2: after the all-gather every rank must hold bit-identical parameters."""
     import torch
     import torch.distributed as dist
-    flats = [fp for (_, fp, _) in sync.flat_sets() if fp is not None]
+    flats = [fs[1] for fs in sync.flat_sets() if fs[1] is not None]
     sums = torch.stack([f.double().sum() for f in flats] + [f.double().abs().sum() for f in flats])
     gathered = [torch.empty_like(sums) for _ in range(world)]
     dist.all_gather(gathered, sums)

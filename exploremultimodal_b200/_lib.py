@@ -92,7 +92,7 @@ _SIGNATURES = {
     'mome_ce_bwd': (C.c_int, [_P, _L, _I, _I, _P, _L, _P, _P, _P]),
     'mome_text_embed_fwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P, C.c_uint32, _F, _P]),
     'mome_text_embed_ws_bytes': (C.c_size_t, [_I]),
-    'mome_text_embed_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, C.c_uint32, _F, _P, C.c_size_t, _P]),
+    'mome_text_embed_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _L, _P, C.c_uint32, _F, _P, C.c_size_t, _P]),
     'mome_adamw_flat': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _L, _P]),
     'mome_sumsq': (C.c_int, [_P, _L, _P, _P]),
     'mome_block_fwd': (C.c_int, [C.POINTER(BlockArgs), _P]),

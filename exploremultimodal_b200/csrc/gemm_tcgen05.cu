@@ -38,11 +38,14 @@ constexpr int PAIR_M = 256;   // rows of a work item (two CTAs x 128)
 constexpr int CTA_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-// Epilogue warps per CTA. The MMAs of a K = 768 tile take ~8k cycles; with 8 epilogue warps (2 per scheduler) the
-// fused epilogues ran at ~0.2 IPC per warp (dependent chains, little to overlap them with) and took ~13k cycles per
-// tile (ncu r02: neither the tensor pipe nor issue slots saturated). Sixteen warps give each scheduler four to
-// interleave. RESIDUAL keeps 8: it holds the fp32 residual prefetch in registers and is HBM-bound at K = 768 anyway.
-constexpr int epi_warps(int epi) { return (epi == MOME_EPI_STORE || epi == MOME_EPI_GELU || epi == MOME_EPI_DGELU) ? 16 : 8; }
+// Epilogue warps per CTA. What bounds the K = 768 GEMMs is the 128 B/clk of the SM's shared-memory data path: the main
+// loop alone moves 2 x 32 KB per k-block through it (TMA fill + tcgen05 operand reads = 96 B/clk at the measured MMA
+// rate), and the epilogue's transpose tile adds 256 KB per 128 x 256 fp32 tile, the whole remaining budget of a tile's
+// ~8k MMA cycles (r02 measurements: TMEM drain only 1560-1600 TFLOP/s, + transpose tile 1560 / 1600 / 1100, + math and
+// stores 1216 / 979 / 921 for STORE / GELU / DGELU). More epilogue warps therefore buy little: 16 (with a 4-stage ring
+// instead of 5 to pay for their transpose tiles) measured +3 % on GELU, whose fp16 math is latency bound as well, and
+// -3 .. -7 % on the STORE and DGELU variants, which keep 8.
+constexpr int epi_warps(int epi) { return epi == MOME_EPI_GELU ? 16 : 8; }
 constexpr int gemm_threads(int epi) { return 128 + 32 * epi_warps(epi); }
 constexpr int kAtomBytes = BLOCK_K * 128;  // one 64x64 MN-major box / 64 rows of a K-major tile
 constexpr int kStagePitch = 36;            // floats per row of the per-warp transpose tile (32 + pad, 16 B aligned)
@@ -326,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
         // DGELU: the stashed bf16 gelu'(z) (8 B per lane-iteration), RESIDUAL: the fp32 residual (16 B per
         // lane-iteration): the first two 32-column chunks up front, then two chunks ahead of their use (three deep was measured:
         // 908 against 921 TFLOP/s, the extra registers cost more than the loads' exposed latency).
-        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks <= 2 ? 1 : 2) : 1;  // 16 epilogue warps: one chunk ahead, 96 registers
+        constexpr int kAuxDepth = EPI == MOME_EPI_DGELU ? (kChunks < 2 ? kChunks : 2) : 1;
         constexpr int kResDepth = EPI == MOME_EPI_RESIDUAL ? 2 : 1;
         uint2 aux[kAuxDepth][8];
         float4 res[kResDepth][8];

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) text_embed_bwd_kernel(const float* __rest
                                                              const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, float* __restrict__ dword,
                                                              float* __restrict__ dpos, float* __restrict__ ws, int rows, int T, int d,
-                                                             const uint32_t* __restrict__ seed, uint32_t salt, uint32_t thr) {
+                                                             const uint32_t* __restrict__ seed, uint32_t salt, uint32_t thr, long long pad_id) {
   extern __shared__ float sacc[];  // [4][d]: dgamma, dbeta, dtype0, dmodal0 of this CTA
   for (int i = threadIdx.x; i < 4 * d; i += 256) sacc[i] = 0.f;
   __syncthreads();
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) text_embed_bwd_kernel(const float* __rest
       if (c < nv) {
         const float4 de = make_float4(rs * (gy[i].x - m1 - xh[i].x * m2), rs * (gy[i].y - m1 - xh[i].y * m2),
                                       rs * (gy[i].z - m1 - xh[i].z * m2), rs * (gy[i].w - m1 - xh[i].w * m2));
-        atomicAdd(reinterpret_cast<float4*>(dword + id * d) + c, de);
+        if (id != pad_id) atomicAdd(reinterpret_cast<float4*>(dword + id * d) + c, de);  // nn.Embedding(padding_idx): no gradient
         atomicAdd(reinterpret_cast<float4*>(dpos + static_cast<long long>(t) * d) + c, de);
         a_t[i].x += de.x; a_t[i].y += de.y; a_t[i].z += de.z; a_t[i].w += de.w;
       }
@@ -323,8 +323,8 @@ extern "C" size_t mome_text_embed_ws_bytes(int32_t d) { return static_cast<size_
 
 extern "C" int mome_text_embed_bwd(const float* dy, const int64_t* ids, const float* xhat, const float* rstd, const float* ln_w,
                                    float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b, float* dmodal0, int64_t rows,
-                                   int32_t T, int32_t d, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* ws,
-                                   size_t ws_bytes, void* stream) {
+                                   int32_t T, int32_t d, int64_t padding_idx, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p,
+                                   void* ws, size_t ws_bytes, void* stream) {
   MOME_REQUIRE(dy && ids && xhat && rstd && ln_w && dword && dpos, "text_embed_bwd: null argument");
   MOME_REQUIRE(d % 4 == 0 && d <= kEmbMaxV4 * 128, "text_embed_bwd: d=%d unsupported", d);
   MOME_REQUIRE(ws != nullptr && ws_bytes >= mome_text_embed_ws_bytes(d), "text_embed_bwd: workspace of %zu bytes needed", mome_text_embed_ws_bytes(d));
@@ -334,7 +334,7 @@ extern "C" int mome_text_embed_bwd(const float* dy, const int64_t* ids, const fl
   const bool drop = drop_seed != nullptr && drop_p > 0.f;
   text_embed_bwd_kernel<<<grid, 256, 4 * d * sizeof(float), s>>>(dy, reinterpret_cast<const long long*>(ids), xhat, rstd, ln_w, dword, dpos,
                                                                   static_cast<float*>(ws), static_cast<int>(rows), T, d,
-                                                                  drop ? drop_seed : nullptr, drop_salt, drop_threshold(drop_p));
+                                                                  drop ? drop_seed : nullptr, drop_salt, drop_threshold(drop_p), padding_idx);
   int rc = check_launch("text_embed_bwd");
   if (rc != MOME_OK) return rc;
   embed_reduce_kernel<<<(4 * d + 255) / 256, 256, 0, s>>>(static_cast<const float*>(ws), grid, d, dln_w, dln_b, dtype0, dmodal0);

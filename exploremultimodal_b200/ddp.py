@@ -62,15 +62,18 @@ class GradSync:
 
     def _flatten(self, ps):
         if not ps:
-            self._sets.append((None, None, ps))
+            self._sets.append((None, None, ps, []))
             return None
-        n = sum(p.numel() for p in ps)
-        pad = 4 * self.world                      # shards of equal size whose starts stay 16-byte aligned
+        ALIGN = 32                                 # every tensor starts on a 128-byte boundary: libmome's kernels use 128-bit
+        offs, n = [], 0                            # (and TMA) accesses on parameters and on .grad (a scalar like itc_temp would
+        for p in ps:                               # otherwise misalign everything behind it)
+            offs.append(n)
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        pad = ALIGN * self.world                   # shards of equal size with aligned starts
         n_pad = (n + pad - 1) // pad * pad
         flat = torch.zeros(n_pad, dtype=torch.float32, device=ps[0].device)
         flat_p = torch.zeros(n_pad, dtype=torch.float32, device=ps[0].device) if self.flatten_params else None
-        off = 0
-        for p in ps:
+        for p, off in zip(ps, offs):
             view = flat[off:off + p.numel()].view_as(p)
             p.grad = view
             self._views.append((p, view))
@@ -80,12 +83,12 @@ class GradSync:
                     pv = flat_p[off:off + p.numel()].view_as(p)
                     pv.copy_(p.detach())
                     p.data = pv
-            off += p.numel()
-        self._sets.append((flat, flat_p, ps))
+        self._sets.append((flat, flat_p, ps, offs))
         return flat
 
     def flat_sets(self):
-        """(flat gradient buffer, flat parameter buffer or None, parameters) per buffer: blocks first, then the rest."""
+        """(flat gradient buffer, flat parameter buffer or None, parameters, element offset of each parameter) per buffer:
+        blocks first, then the rest."""
         return list(self._sets)
 
     def zero_grad(self):

@@ -67,16 +67,15 @@ class FlatAdamW:
                 gid_of[id(p)] = gi
         self.bufs = []   # per flat buffer: dict(p, g, gid, m, v, lo, hi)
         dev = None
-        for flat_g, flat_p, ps in sync.flat_sets():
+        for flat_g, flat_p, ps, offs in sync.flat_sets():
             if flat_g is None:
                 continue
+            assert flat_p is not None, 'FlatAdamW needs GradSync(..., flatten_params=True)'
             dev = flat_g.device
-            gid = torch.zeros(flat_g.numel(), dtype=torch.uint8, device=dev)
-            off = 0
-            for p in ps:
+            gid = torch.zeros(flat_g.numel(), dtype=torch.uint8, device=dev)   # alignment padding: group 0, zero gradients
+            for p, off in zip(ps, offs):
                 assert id(p) in gid_of, 'every trainable parameter must be in a parameter group'
                 gid[off:off + p.numel()] = gid_of[id(p)]
-                off += p.numel()
             n = flat_g.numel()
             lo, hi = (self.rank * (n // self.world), (self.rank + 1) * (n // self.world)) if self.zero2 else (0, n)
             self.bufs.append(dict(p=flat_p, g=flat_g, gid=gid, lo=lo, hi=hi,

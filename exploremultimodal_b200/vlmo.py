@@ -141,6 +141,7 @@ class _TextEmbedFn(torch.autograd.Function):
     def backward(ctx, dy):
         ids, xhat, rstd, ln_w = ctx.saved_tensors
         B, T, d, wshape, pshape, tshape, mshape, drop, holder = ctx.meta
+        pad_id = holder.word_embeddings.padding_idx if holder.word_embeddings.padding_idx is not None else -1
         dev = dy.device
         dy = dy.reshape(B * T, d).float().contiguous()
         word, pos = ctx.params
@@ -162,7 +163,7 @@ class _TextEmbedFn(torch.autograd.Function):
         seed, salt, p = drop if drop else (None, 0, 0.0)
         L.check(L.lib().mome_text_embed_bwd(dy.data_ptr(), ids.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), ln_w.data_ptr(),
                                             dword.data_ptr(), dpos.data_ptr(), dtype_w.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
-                                            dmodal_w.data_ptr(), B * T, T, d, seed.data_ptr() if seed is not None else None, salt, p,
+                                            dmodal_w.data_ptr(), B * T, T, d, pad_id, seed.data_ptr() if seed is not None else None, salt, p,
                                             ws.data_ptr(), ws.numel(), L.stream()), 'mome_text_embed_bwd')
         return None, ret_word, ret_pos, dtype_w, dln_w, dln_b, dmodal_w, None, None, None
 

@@ -288,8 +288,8 @@ int mome_text_embed_fwd(const int64_t* ids, const float* word, const float* pos,
 size_t mome_text_embed_ws_bytes(int32_t d);
 int mome_text_embed_bwd(const float* dy, const int64_t* ids, const float* xhat, const float* rstd, const float* ln_w,
                         float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b, float* dmodal0, int64_t rows,
-                        int32_t T, int32_t d, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* ws,
-                        size_t ws_bytes, void* stream);
+                        int32_t T, int32_t d, int64_t padding_idx /* row of `word` that receives no gradient, -1 = none */,
+                        const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Optimizer step on flat buffers -------------------------------------------------------
  * reference: apex FusedAdam / DeepSpeed Adam(adam_w_mode) built by utils/optim_factory.py:93-199 over the three-tier

@@ -209,7 +209,10 @@ def test_gradsync_flat_buffers_back_every_gradient():
     assert len(sync.block_flat) == len(model.transformer.blocks)
     total = sum(f.numel() for f in sync.block_flat) + sync.rest_flat.numel()
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    assert n_train <= total < n_train + 4 * (len(sync.block_flat) + 1)   # each buffer is padded to a multiple of 4 * world elements
+    n_tensors = sum(1 for p in model.parameters() if p.requires_grad)
+    assert n_train <= total <= n_train + 32 * (n_tensors + len(sync.block_flat) + 1)   # every tensor starts on a 128-byte boundary
+    for flat, _, ps, offs in sync.flat_sets():
+        assert all(o % 32 == 0 for o in offs) and all(p.grad.data_ptr() == flat.data_ptr() + 4 * o for p, o in zip(ps, offs))
     for blk, flat in zip(model.transformer.blocks, sync.block_flat):
         assert blk.fused_grad_accumulation and blk.grads_ready_hook is None
         lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
