@@ -50,6 +50,11 @@ constexpr int gemm_threads(int epi) { return 128 + 32 * epi_warps(epi); }
 constexpr int kAtomBytes = BLOCK_K * 128;  // one 64x64 MN-major box / 64 rows of a K-major tile
 constexpr int kStagePitch = 36;            // floats per row of the per-warp transpose tile (32 + pad, 16 B aligned)
 constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
+constexpr int kStage16BytesPerWarp = 32 * 64;  // bf16 transpose tile: 32 rows x 32 columns, 16-byte pieces XOR-swizzled
+// Variants whose epilogue consumes bf16(acc + bias) — STORE, GELU (the reference's autocast Linear hands bf16 to the
+// activation) and RESIDUAL (b = bf16(acc + bias) is the branch value) — add the bias in the accumulator's row layout
+// and stage bf16: half the bytes through the SM's shared-memory data path, which is what bounds the K = 768 GEMMs.
+constexpr bool stage16(int epi) { return epi == MOME_EPI_STORE || epi == MOME_EPI_GELU || epi == MOME_EPI_RESIDUAL; }
 
 struct GemmGroupDev {
   void* out;
@@ -149,15 +154,16 @@ __device__ __forceinline__ void gelu_fast2(float z0, float z1, float m0, float m
   dg_bf16x2 = pack_bf16(dgf.x, dgf.y);
 }
 
-template <int BLOCK_N, int EW>
+template <int BLOCK_N, int EW, bool S16>
 struct GemmCfg {
   static constexpr int A_BYTES = CTA_M * 128;            // this CTA's 128 rows x 64 k
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;    // this CTA's half of the N tile x 64 k
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // the ring shares the 227 KB with one transpose tile per epilogue warp
-  static constexpr int STAGES = (BLOCK_N == 256) ? (EW == 16 ? 4 : 5) : (EW == 16 ? 6 : 7);
+  static constexpr int STAGES = (BLOCK_N == 256) ? ((EW == 16 && !S16) ? 4 : 5) : ((EW == 16 && !S16) ? 6 : 7);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int EPI_BYTES = EW * kStageBytesPerWarp;
+  static constexpr int STAGE_TILE_BYTES = S16 ? kStage16BytesPerWarp : kStageBytesPerWarp;
+  static constexpr int EPI_BYTES = EW * STAGE_TILE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -167,7 +173,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
   constexpr int kEpiWarps = epi_warps(EPI);
   constexpr int kParts = kEpiWarps / 4;            // column parts of a tile (one per group of 4 warps = 128 TMEM lanes)
   constexpr int kPartCols = BLOCK_N / kParts;
-  using Cfg = GemmCfg<BLOCK_N, kEpiWarps>;
+  constexpr bool S16 = stage16(EPI);
+  using Cfg = GemmCfg<BLOCK_N, kEpiWarps, S16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -291,7 +298,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
     const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int part = ew >> 2;              // which column part of the tile
-    const uint32_t stage_u32 = smem_u32(epi_stage + ew * (kStageBytesPerWarp / 4));  // this warp's transpose tile
+    const uint32_t stage_u32 = smem_u32(epi_stage + ew * (Cfg::STAGE_TILE_BYTES / 4));  // this warp's transpose tile
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -369,15 +376,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
           }
           if (p.debug & 2) continue;  // measurement knob: TMEM drain only
-          const uint32_t mine = stage_u32 + lane * (kStagePitch * 4);
+          if (S16) {
+            // lane = row: add the bias of the chunk's 32 columns (the same for every lane: broadcast loads), round to
+            // bf16 and store the row's 64 bytes as four 16-byte pieces, piece p at p ^ ((row >> 1) & 3)
+            const bool has_bias = g.bias != nullptr && (FULL || c < nchunks);
+            const float* bp = g.bias + (col_base - c4 + c * 32);
+            uint32_t w[16];
   #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            sts_v4_u32(mine + 16 * i, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) {
+              float4 b4r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_bias) b4r = __ldg(reinterpret_cast<const float4*>(bp) + i);
+              w[2 * i] = pack_bf16(__uint_as_float(r[4 * i]) + b4r.x, __uint_as_float(r[4 * i + 1]) + b4r.y);
+              w[2 * i + 1] = pack_bf16(__uint_as_float(r[4 * i + 2]) + b4r.z, __uint_as_float(r[4 * i + 3]) + b4r.w);
+            }
+            const uint32_t mine16 = stage_u32 + lane * 64;
+            const int sw = (lane >> 1) & 3;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) sts_v4_u32(mine16 + ((i ^ sw) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          } else {
+            const uint32_t mine = stage_u32 + lane * (kStagePitch * 4);
+  #pragma unroll
+            for (int i = 0; i < 8; ++i)
+              sts_v4_u32(mine + 16 * i, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          }
           __syncwarp();
           if ((p.debug & 1) || (!FULL && c >= nchunks)) { __syncwarp(); continue; }  // knob: no epilogue math / global IO
           const int col = col_base + c * 32;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (EPI != MOME_EPI_ATOMIC && EPI != MOME_EPI_DGELU && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+          if (!S16 && EPI != MOME_EPI_ATOMIC && EPI != MOME_EPI_DGELU && g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col));
           if (EPI == MOME_EPI_RESIDUAL && p.gamma != nullptr) gm4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
           const uint32_t lds_a = stage_u32 + (rsub * kStagePitch + c4) * 4;
@@ -386,11 +412,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
   #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (FULL || it < nvalid) {
-              float4 v = lds_v4(lds_a + it * (16 * kStagePitch));
+              float4 v;
+              if (S16) {  // row rsub + 4 it, this lane's 4 columns = 8 bytes: piece (c4 >> 3) of the row, swizzled as written
+                const int row = rsub + 4 * it;
+                v = unpack4_bf16(lds_v2_u32(stage_u32 + row * 64 + ((((c4 >> 3) ^ ((row >> 1) & 3)) << 4) | ((c4 & 4) << 1))));
+              } else {
+                v = lds_v4(lds_a + it * (16 * kStagePitch));
+              }
               if (EPI == MOME_EPI_ATOMIC) {
                 atomicAdd(reinterpret_cast<float4*>(op), v);
               } else {
-                if (EPI != MOME_EPI_DGELU) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                if (!S16 && EPI != MOME_EPI_DGELU) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
                 if (EPI == MOME_EPI_GELU) {
                   // out = gelu(z), out2 = gelu'(z), both from the fp32 accumulator + bias rounded once to fp16 (the
                   // reference's autocast rounds z to bf16 first; fp16 keeps 3 more bits of it)
@@ -534,7 +566,7 @@ std::vector<ProfRec> g_prof;
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DROP = false>
 int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, epi_warps(EPI)>;
+  using Cfg = GemmCfg<BLOCK_N, epi_warps(EPI), stage16(EPI)>;
   static bool configured = false;
   auto kern = gemm_pair_kernel<BLOCK_N, A_MN, B_MN, EPI, DROP>;
   if (!configured) {

@@ -25,6 +25,11 @@ __device__ __forceinline__ void sts_v4(uint32_t saddr, float4 v) {
 __device__ __forceinline__ void sts_v4_u32(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint2 lds_v2_u32(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
