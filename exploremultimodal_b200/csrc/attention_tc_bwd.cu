@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 
 // GW = warps of the P / dS group: 8 (a thread owns a query row x 64 keys of the block) or 16 (x 32 keys). The P / dS
 // phase is a serial per-thread chain of exponentials between two tensor-core phases; with 16 warps it is half as long
-// and each scheduler has four warps to interleave (MOME_ATTN_TC_BWD=1 selects 8, the default 3 selects 16).
+// and each scheduler has four warps to interleave — yet it measured no faster (404 vs 405 us at 256 x [40 | 197] without
+// dropout, 509 vs 478 us with): the block's chain is bound by the tensor-core / barrier latencies between its phases, not by
+// the exponentials. 8 warps stay the default; MOME_ATTN_TC_BWD=3 selects 16.
 // EARLY_S (experimental, MOME_ATTN_TC_BWD=2, 8 warps): S / dP of the next block of the item are issued before the
 // accumulate MMAs of the current one (measured: no gain, 412 vs 405 us).
 template <int N>
@@ -509,7 +511,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   }
   const char* variant = getenv("MOME_ATTN_TC_BWD");
   const bool early_s = variant != nullptr && variant[0] == '2';
-  const bool wide = variant == nullptr || variant[0] == '3';  // 16 P / dS warps; "1" / "2" keep 8
+  const bool wide = variant != nullptr && variant[0] == '3';  // 16 P / dS warps (measured: 404 vs 405 us without, 509 vs 478 us with dropout: no gain)
   BwdParams p;
   const int64_t d = static_cast<int64_t>(H) * kHd, d3 = 3 * d;
   int rc = tma_encode_bf16_2d(&p.qkv32, qkv, d3, tokens, d3, kHd, 32);
