@@ -65,6 +65,7 @@ def parse():
                     help="'flat': exploremultimodal_b200.optim.FlatAdamW (one mome_adamw_flat launch per flat buffer, gradient clipping "
                          "at 5.0 fused, the reference's three-tier parameter groups); 'torch': torch.optim.AdamW(fused=True)")
     ap.add_argument('--zero2', action='store_true', help='ZeRO-2 style: reduce-scatter gradients, shard Adam state, all-gather parameters (N > 1)')
+    ap.add_argument('--no-overlap', action='store_true', help='reduce all gradients after the backward instead of block by block during it (N > 1)')
     ap.add_argument('--reduce-dtype', default='fp32', choices=['fp32', 'bf16'], help='dtype of the gradient all-reduce (N > 1)')
     ap.add_argument('--dedup', action='store_true',
                     help='opt-in cross-pass de-duplication of the pre-fusion layers (config.train.dedup_prefix, SURVEY.md 8(f) N3): '
@@ -376,7 +377,8 @@ def run_mome(args):
     if world > 1:
         # the persistent GEMMs own every SM: keep NCCL's all-reduce to a few CTAs so that it co-runs instead of
         # displacing GEMM cluster pairs (NVLS reduces in the switch, few channels already saturate NVLink)
-        os.environ.setdefault('NCCL_MAX_CTAS', '8')
+        if not args.no_overlap:
+            os.environ.setdefault('NCCL_MAX_CTAS', '8')
         os.environ.setdefault('MOME_ITC_GATHER', 'auto')
         dist.init_process_group('nccl', device_id=dev)
 
@@ -408,7 +410,7 @@ def run_mome(args):
     zero2 = args.zero2 and world > 1 and args.optimizer == 'flat'
     # flat per-block gradient (and parameter) buffers, reduced / reduce-scattered as blocks finish their backward
     sync = GradSync(model, world, reduce_dtype=args.reduce_dtype, reduce='reduce_scatter' if zero2 else 'all_reduce',
-                    flatten_params=args.optimizer == 'flat')
+                    flatten_params=args.optimizer == 'flat', overlap=not args.no_overlap)
     if args.optimizer == 'flat':
         # hyper-parameters of the reference's pretraining recipe (conf/train/pretrain_mum.yaml: AdamW betas (0.9, 0.98), eps 1e-6,
         # weight decay 0.05, clip_grad 5.0; lr multipliers 1) over get_parameter_groups' three tiers
@@ -594,6 +596,7 @@ def run_mome(args):
         config['itc_parity'] = checks.get('itc_parity')
         config['grad_sync'] = checks.get('grad_sync')
         config['grad_reduce_dtype'] = args.reduce_dtype
+        config['grad_reduce_overlap'] = not args.no_overlap
         config['param_sync'] = checks.get('param_sync')
     config['optimizer'] = ('FlatAdamW (mome_adamw_flat, clip 5.0 fused' + (', ZeRO-2 sharded state' if zero2 else '') + ')') if args.optimizer == 'flat' else 'torch.optim.AdamW(fused)'
     if world > 1:

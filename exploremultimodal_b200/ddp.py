@@ -24,10 +24,13 @@ import torch.distributed as dist
 
 class GradSync:
 
-    def __init__(self, model, world, reduce_dtype='fp32', reduce='all_reduce', flatten_params=False):
+    def __init__(self, model, world, reduce_dtype='fp32', reduce='all_reduce', flatten_params=False, overlap=True):
         """reduce: 'all_reduce' (DDP: every rank ends with the mean gradient) or 'reduce_scatter' (ZeRO-2: rank r ends
         with the mean of elements [r n / W, (r + 1) n / W) of every flat buffer only; the rest of the buffer is scratch).
-        flatten_params: also move every parameter's storage into a flat fp32 buffer per block (optim.FlatAdamW)."""
+        flatten_params: also move every parameter's storage into a flat fp32 buffer per block (optim.FlatAdamW).
+        overlap: True = reduce each block's buffer on a side stream as soon as its last backward of the step has been issued;
+        False = reduce everything in finish(), after the backward (the persistent GEMMs own every SM, so a concurrent NCCL
+        kernel displaces GEMM CTA pairs: measured at N = 2)."""
         assert reduce_dtype in ('fp32', 'bf16') and reduce in ('all_reduce', 'reduce_scatter')
         assert not (reduce == 'reduce_scatter' and reduce_dtype != 'fp32')
         self.world = world
@@ -49,7 +52,7 @@ class GradSync:
             flat = self._flatten(ps)
             in_block.update(id(p) for p in ps)
             blk.fused_grad_accumulation = True
-            blk.grads_ready_hook = self._on_block_ready if world > 1 else None
+            blk.grads_ready_hook = self._on_block_ready if (world > 1 and overlap) else None
             blk._flat_grad = flat
             blk._pending_bwd = 0
             self.blocks.append((blk, ps))
