@@ -375,10 +375,7 @@ def run_mome(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # the persistent GEMMs own every SM: keep NCCL's all-reduce to a few CTAs so that it co-runs instead of
-        # displacing GEMM cluster pairs (NVLS reduces in the switch, few channels already saturate NVLink)
-        if not args.no_overlap:
-            os.environ.setdefault('NCCL_MAX_CTAS', '8')
+        # (capping NCCL's CTAs was measured at N = 2: NCCL_MAX_CTAS=8 128.1 ms, 32 126.1 ms per step: left at NCCL's default)
         os.environ.setdefault('MOME_ITC_GATHER', 'auto')
         dist.init_process_group('nccl', device_id=dev)
 

@@ -74,9 +74,7 @@ constexpr int kStages = 2;
 constexpr int kMetaOff = kStages * kStageBytes;   // per stage 64 B: keep words [8], seq desc [4]
 constexpr int kBarOff = kMetaOff + kStages * 64;  // 12 barriers, TMEM slot
 constexpr int kXchgOff = kBarOff + 128;            // row max / row sum exchange between the two threads of a row: 2 x 2 KB
-constexpr int kLenOff = kXchgOff + 4096;             // sequence lengths of this CTA's first kLenCap items (filled once at kernel start)
-constexpr int kLenCap = 512;
-constexpr int kFwdSmem = kLenOff + kLenCap * 4 + 1024;
+constexpr int kFwdSmem = kXchgOff + 4096 + 1024;
 constexpr int kFwdThreads = 64 + 2 * 256;         // producer, MMA, 2 softmax groups of 8 warps
 constexpr uint32_t kSlotCols = 256, kOCol = 64, kPHiCol = 128;
 
@@ -132,10 +130,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
 
   // stale shared memory must at least be finite: rows between the last box and n_pad multiply p = 0
   for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kFwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  // Lengths of the sequences this CTA will visit: the MMA issuer and both softmax groups need them to walk the units;
-  // read from global memory item by item, every item change stalled the single MMA-issuing thread for an L2 round trip.
-  int* nlen = reinterpret_cast<int*>(smem + kLenOff);
-  for (int k = threadIdx.x; k < kLenCap && blockIdx.x + k * G < p.num_items; k += kFwdThreads) nlen[k] = seq_len(p.seq_desc, (blockIdx.x + k * G) / H);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 2);
@@ -233,10 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
     // lane test every tcgen05.mma was wrapped in an R2UR waterfall loop, ~220 cycles per instruction (tools/umma_probe.cu).
     if (elect_one()) {
       const int first = blockIdx.x;
-      auto item_n = [&](int k) {
-        if (first + k * G >= p.num_items) return 0;
-        return k < kLenCap ? nlen[k] : seq_len(p.seq_desc, (first + k * G) / H);
-      };
+      auto item_n = [&](int k) { return first + k * G < p.num_items ? seq_len(p.seq_desc, (first + k * G) / H) : 0; };
       struct It { int k, t, u, n; };  // local item, tile, unit number, sequence length (0: past the end)
       auto advance = [&](It& it) {
         ++it.u;
@@ -316,7 +307,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
     int u = 0, k = 0;
     for (int item = blockIdx.x; item < p.num_items; item += G, ++k) {
       const int s = item / H, h = item - s * H;
-      const int n = k < kLenCap ? nlen[k] : seq_len(p.seq_desc, s);
+      const int n = seq_len(p.seq_desc, s);
       const int tiles = n > kQTile ? 2 : 1;
       for (int t = 0; t < tiles; ++t, ++u) {
         if ((u & 1) != g) continue;

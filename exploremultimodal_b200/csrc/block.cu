@@ -40,8 +40,8 @@ extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
   const bool path = on(a, a->p_path);
   if (path) {
     MOME_REQUIRE(a->row_sample != nullptr && a->row_scale1 != nullptr && a->row_scale2 != nullptr, "block_fwd: stochastic depth needs row_sample / row_scale buffers");
-    MOME_TRY(mome_droppath_scales(a->row_sample, T, a->drop_seed, a->drop_salt + 4, a->p_path, a->row_scale1, stream));
-    MOME_TRY(mome_droppath_scales(a->row_sample, T, a->drop_seed, a->drop_salt + 5, a->p_path, a->row_scale2, stream));
+    MOME_TRY(mome::droppath_scales2(a->row_sample, T, a->drop_seed, a->drop_salt + 4, a->drop_salt + 5, a->p_path, a->row_scale1, a->row_scale2,
+                                    static_cast<cudaStream_t>(stream)));
   }
   MOME_TRY(mome_ln_fwd(a->x, a->n1w, a->n1b, a->h, dt, a->mean1, a->rstd1, T, d, a->eps, stream));
   {

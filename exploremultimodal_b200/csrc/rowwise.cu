@@ -406,6 +406,30 @@ __global__ void droppath_scales_kernel(const int32_t* __restrict__ row_sample, l
     out[r] = (drop_mix(static_cast<uint32_t>(row_sample[r]), key) >> 8) >= thr ? keep : 0.f;
 }
 
+// both branches of a block (salts differ) in one launch: internal to block.cu
+__global__ void droppath_scales2_kernel(const int32_t* __restrict__ row_sample, long long rows, const uint32_t* __restrict__ seed,
+                                        uint32_t salt1, uint32_t salt2, float p, float* __restrict__ out1, float* __restrict__ out2) {
+  const uint32_t s = __ldg(seed);
+  const uint32_t key1 = drop_mix(salt1, s), key2 = drop_mix(salt2, s);
+  const uint32_t thr = static_cast<uint32_t>(p * 16777216.f);
+  const float keep = 1.f / (1.f - p);
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t smp = static_cast<uint32_t>(row_sample[r]);
+    out1[r] = (drop_mix(smp, key1) >> 8) >= thr ? keep : 0.f;
+    out2[r] = (drop_mix(smp, key2) >> 8) >= thr ? keep : 0.f;
+  }
+}
+namespace mome {
+int droppath_scales2(const int32_t* row_sample, int64_t rows, const uint32_t* seed, uint32_t salt1, uint32_t salt2, float p, float* out1,
+                     float* out2, cudaStream_t stream) {
+  MOME_REQUIRE(p >= 0.f && p < 1.f && seed != nullptr, "droppath_scales: need 0 <= p < 1 and a seed");
+  if (rows == 0) return MOME_OK;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, sm_count() * 4LL)));
+  droppath_scales2_kernel<<<grid, 256, 0, stream>>>(row_sample, rows, seed, salt1, salt2, p, out1, out2);
+  return check_launch("droppath_scales2");
+}
+}  // namespace mome
+
 static int col_threads(int64_t d) { return static_cast<int>(((d / 4) + 31) / 32 * 32); }
 static int col_grid(int64_t rows, int ctas_per_sm, int rows_per_iter = kColRows) {
   const long long groups = (rows + rows_per_iter - 1) / rows_per_iter;

@@ -150,6 +150,7 @@ class GradSync:
                 if id(blk) in self._fired and self.comm is not None:  # a stale buffer went out earlier: wait for it first
                     torch.cuda.current_stream().wait_stream(self.comm)
                 self._all_reduce(blk._flat_grad)
+        used_comm = bool(self._fired)      # nothing was enqueued on the side stream in a step reduced after the backward
         self._fired.clear()
         if self.rest:
             self._rebind(self.rest)
@@ -157,5 +158,5 @@ class GradSync:
             return
         if self.rest_flat is not None:
             self._all_reduce(self.rest_flat)
-        if self.comm is not None:
+        if self.comm is not None and used_comm:
             torch.cuda.current_stream().wait_stream(self.comm)

@@ -50,7 +50,7 @@ def mlm_from_feats(model, txt_feats, labels, txt_ids):
     cap = getattr(model.config.train, 'mlm_capacity', 0.25)
     K = B * T if B * T <= 256 else min(B * T, max(256, int(cap * B * T)))
     order, tgt, overflow = compact_masked_rows(flat, K)
-    rows = txt_feats.reshape(B * T, d)[order]
+    rows = torch.index_select(txt_feats.reshape(B * T, d), 0, order)  # backward = index_add_ (advanced indexing's is a 360 us sort-based kernel)
     tr = model.transformer
     if tr.precision == 'bf16' and getattr(model.config.train, 'fused_mlm_head', True) and d % 64 == 0:
         # decoder GEMM (tcgen05) + cross-entropy + accuracy with the [K, vocab] logits kept once, in bf16, and turned into

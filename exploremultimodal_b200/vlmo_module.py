@@ -172,10 +172,10 @@ class VlmoModule(nn.Module):
             idx = batch['_prefix_index'] if '_prefix_index' in batch else None
             img_pre = txt_pre = None
             if img is not None:
-                img_pre = pre['img'] if idx is None else pre['img'][idx[0]]
+                img_pre = pre['img'] if idx is None else torch.index_select(pre['img'], 0, idx[0])
             if txt_ids is not None:
                 txt_pre = pre['txt_mlm' if mask_txt else 'txt']
-                txt_pre = txt_pre if idx is None else txt_pre[idx[1]]
+                txt_pre = txt_pre if idx is None else torch.index_select(txt_pre, 0, idx[1])
             co_feats, _ = transformer.forward_features_from_prefix(img_pre=img_pre, txt_pre=txt_pre,
                                                                    img_attn_masks=img_attn_masks,
                                                                    txt_attn_masks=txt_attn_masks)
