@@ -242,7 +242,7 @@ def attention_preflight(batch, device):
     tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'attn_bench.py')
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT')}
     try:
-        r = subprocess.run([sys.executable, tool, '--check', '--tc-bwd', '1', '--iters', '1', '--batch', str(min(2 * batch, 256)), '--device', str(device)],
+        r = subprocess.run([sys.executable, tool, '--check', '--tc-bwd', 'p', '--iters', '1', '--batch', str(min(2 * batch, 256)), '--device', str(device)],
                            env=env, capture_output=True, text=True, timeout=180)
         ok = r.returncode == 0 and 'CHECK OK' in r.stdout
         detail = '' if ok else (r.stdout[-300:] + r.stderr[-300:])

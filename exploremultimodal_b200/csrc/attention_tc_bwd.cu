@@ -494,6 +494,15 @@ int opt_in(K kern, int bytes, const char* what) {
 
 }  // namespace
 
+int attn_delta_launch(const void* out, const void* dout, const int32_t* seq_desc, float* delta, int H, int max_seq_len, int num_seqs,
+                      cudaStream_t stream) {
+  const long long rows = static_cast<long long>(num_seqs) * max_seq_len;
+  attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                                static_cast<const __nv_bfloat16*>(dout), seq_desc, delta, H,
+                                                                                max_seq_len, num_seqs);
+  return check_launch("attn_delta");
+}
+
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask, const float* lse,
                 void* dqkv, float* delta_ws, int64_t tokens, int num_seqs, int max_seq_len, int H, float scale, const uint32_t* drop_seed,
                 uint32_t drop_salt, float drop_p, cudaStream_t stream) {
@@ -533,10 +542,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_
   p.drop_seed = drop_seed;
   p.drop_salt = drop_salt;
   p.drop_thr = drop_threshold(drop_p);
-  const long long rows = static_cast<long long>(num_seqs) * max_seq_len;
-  attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), p.dout, seq_desc, delta_ws, H,
-                                                                                max_seq_len, num_seqs);
-  rc = check_launch("attn_delta");
+  rc = attn_delta_launch(out, dout, seq_desc, delta_ws, H, max_seq_len, num_seqs, stream);
   if (rc != MOME_OK) return rc;
   const int grid = std::min(p.num_items, sm_count());
   const bool drop = drop_seed != nullptr && drop_p > 0.f;

@@ -370,15 +370,76 @@ def test_attention_tcgen05_forward_matches_mma_sync(drop, mask_kind, monkeypatch
         valid[s0:s0 + n0_] = True
         valid[s1:s1 + n1_] = True
     grads = {}
-    for bwd in ('0', '1'):
+    for bwd in ('0', '1', 'p'):   # mma.sync pair, first tcgen05 kernel, software-pipelined tcgen05 kernel (the default)
         monkeypatch.setenv('MOME_ATTN_TC_BWD', bwd)
         n0 = L.lib().mome_launch_count()
         grads[bwd] = ops.attn_bwd(qkv, o0, dout, lay, mask, l0, H, 0.125, dr)
         assert L.lib().mome_launch_count() == n0 + 2     # dq + dkv kernels, or delta + fused tcgen05 kernel
-    assert torch.isfinite(grads['1'][valid].float()).all()
-    assert rel_err(grads['1'][valid], grads['0'][valid]) < BF16_TOL * 2   # two bf16 pipelines against each other
+    for bwd in ('1', 'p'):
+        assert torch.isfinite(grads[bwd][valid].float()).all()
+        assert rel_err(grads[bwd][valid], grads['0'][valid]) < BF16_TOL * 2   # two bf16 pipelines against each other
+    # same arithmetic per element, different accumulation order inside the tensor core only
+    assert rel_err(grads['p'][valid], grads['1'][valid]) < 2e-3
+    monkeypatch.delenv('MOME_ATTN_TC_BWD')
     g1 = ops.attn_bwd(qkv, o1, dout, lay, mask, l1, H, 0.125, dr)
     assert rel_err(g1[valid], grads['0'][valid]) < BF16_TOL * 2
+
+
+@pytest.mark.parametrize('drop', [False, True])
+@pytest.mark.parametrize('layout', ['split', 'fused', 'gather', 'ragged'])
+def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatch):
+    """The software-pipelined tcgen05 backward with several items per CTA (the operand-tile ring wraps, 1-tile and 2-tile
+    items alternate, TMEM buffers and barriers go through many phases) against the mma.sync pair: same contract, same
+    dropout mask. `gather`: second range not 8-row aligned (cp.async path); `ragged`: lengths 1 .. 256 mixed."""
+    L, ops = _mods()
+    H = 12
+    g = torch.Generator().manual_seed(7)
+    if layout == 'split':
+        lay = ops.split_layout(30, 40, 197, _dev())
+    elif layout == 'fused':
+        lay = ops.fused_layout(40, 40, 197, _dev())
+    else:
+        seqs, row = [], 0
+        n_seq = 48
+        if layout == 'gather':
+            lens = [(13, 100 + (i % 5) * 20) for i in range(n_seq)]
+        else:
+            lens = [(int(a), int(b)) for a, b in zip(torch.randint(1, 41, (n_seq,), generator=g) // 8 * 8 + 8,
+                                                     torch.randint(0, 209, (n_seq,), generator=g))]
+        t0 = 0
+        t1 = sum(a for a, _ in lens)
+        for a, b in lens:
+            seqs.append((t0, a, t1 if b > 0 else 0, b))
+            t0 += a
+            t1 += b
+        tokens = t1
+        desc = torch.tensor(seqs, dtype=torch.int32, device=_dev())
+        lay = ops.PackedLayout(tokens, [(0, tokens, 'vl')], desc, len(seqs), max(a + b for a, b in lens))
+    assert 64 < lay.max_seq_len <= 256 and lay.num_seqs * H > 3 * 148
+    qkv = _rand(lay.tokens, 3 * 64 * H, dtype=torch.bfloat16, seed=21)
+    dout = _rand(lay.tokens, 64 * H, dtype=torch.bfloat16, seed=22)
+    mask = (torch.rand(lay.tokens, generator=g) > 0.15).to(torch.uint8)
+    valid = torch.zeros(lay.tokens, dtype=torch.bool)
+    for (s0, n0_, s1, n1_) in lay.seq_desc.tolist():
+        mask[s0] = 1
+        valid[s0:s0 + n0_] = True
+        valid[s1:s1 + n1_] = True
+    mask, valid = mask.to(_dev()), valid.to(_dev())
+    seed = torch.tensor([91], dtype=torch.int32, device=_dev())
+    dr = (seed, 5, 0.1) if drop else None
+    monkeypatch.setenv('MOME_ATTN_TC', '0')
+    out, lse = ops.attn_fwd(qkv, lay, mask, H, 0.125, dr)
+    grads = {}
+    for bwd in ('0', 'p'):
+        monkeypatch.setenv('MOME_ATTN_TC_BWD', bwd)
+        grads[bwd] = ops.attn_bwd(qkv, out, dout, lay, mask, lse, H, 0.125, dr)
+    assert torch.isfinite(grads['p'][valid].float()).all()
+    d = 64 * H
+    for name, sl in (('dq', slice(0, d)), ('dk', slice(d, 2 * d)), ('dv', slice(2 * d, 3 * d))):
+        assert rel_err(grads['p'][valid][:, sl], grads['0'][valid][:, sl]) < BF16_TOL * 2, name
+    # repeatable: no atomics, no dependence on the schedule
+    again = ops.attn_bwd(qkv, out, dout, lay, mask, lse, H, 0.125, dr)
+    assert torch.equal(again[valid], grads['p'][valid])
 
 
 def test_attention_no_mask_pointer():

@@ -38,7 +38,7 @@ def main():
     ap.add_argument('--tc', default='1', help='MOME_ATTN_TC value to compare against the mma.sync kernels')
     ap.add_argument('--mask', default='ones', choices=['ones', 'random', 'pad'], help='key mask: all ones (the bench), 10 %% random zeros, or padded text (lengths 8..40)')
     ap.add_argument('--tc-bwd', nargs='?', const='1', default=None,
-                    help='MOME_ATTN_TC_BWD value for the second variant (3: tcgen05 backward with 16 P / dS warps = the library default, 1: 8 warps, 2: 8 warps + EARLY_S scheduling); default: mma.sync backward in both')
+                    help='MOME_ATTN_TC_BWD value for the second variant (p: software-pipelined tcgen05 backward = the library default, 1: first tcgen05 kernel, 2: + EARLY_S scheduling, 3: 16 P / dS warps); default: mma.sync backward in both')
     ap.add_argument('--check', action='store_true', help='exit 1 if the two variants disagree (used by bench.py as a pre-flight check)')
     ap.add_argument('--device', type=int, default=0)
     ap.add_argument('--only', default='', help='substring of the layout name to run')
