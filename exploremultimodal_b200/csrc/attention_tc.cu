@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
         for (int g = 0; g < 2; ++g) {
           It& pp = pIt[g];
           It& sp = sIt[g];
-          if (pp.n > 0 && sp.u > pp.u && mbar_try_wait(&p_full[g], (pp.u >> 1) & 1)) {
+          if (pp.n > 0 && sp.u > pp.u && mbar_test_wait(&p_full[g], (pp.u >> 1) & 1)) {
             tcgen05_fence_after();
             const int stage = pp.k & 1;
             const int n_pad = (pp.n + 15) & ~15;
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
             if (pp.n > 0) advance(pp);
             progress = true;
           }
-          if (sp.n > 0 && sp.u == pp.u && mbar_try_wait(&full[sp.k & 1], (sp.k >> 1) & 1) &&
-              mbar_try_wait(&tmem_free[g], ((sp.u >> 1) & 1) ^ 1)) {
+          if (sp.n > 0 && sp.u == pp.u && mbar_test_wait(&full[sp.k & 1], (sp.k >> 1) & 1) &&
+              mbar_test_wait(&tmem_free[g], ((sp.u >> 1) & 1) ^ 1)) {
             tcgen05_fence_after();
             const int stage = sp.k & 1;
             const int n_pad = (sp.n + 15) & ~15;
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
             progress = true;
           }
         }
-        if (!progress) __nanosleep(40);
       }
     }
   } else {

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
       };
       auto keys_of = [](const Cur& c, int j) { return min(kTile, pad16(c.n - j * kTile)); };
       auto slot_addr = [&](uint32_t cnt) { return sR + (cnt & 7) * kTileBytes; };
-      auto tile_ready = [&](uint32_t cnt) { return mbar_try_wait(&B.full[cnt & 7], (cnt >> 3) & 1); };
+      auto tile_ready = [&](uint32_t cnt) { return mbar_test_wait(&B.full[cnt & 7], (cnt >> 3) & 1); };
       Cur S{0, item_n(0), 0, 0, 0, 0, 0};
       S.nt = S.n > kTile ? 2 : 1;
       Cur A = S;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
         if (S.n > 0) {
           const uint32_t buf = nsb & 1;
           const uint32_t tq = S.tb + tile_q(S.i), tk = S.tb + tile_k(S.j, S.nt);
-          if (mbar_try_wait(&B.sdp_free[buf], ((nsb >> 1) & 1) ^ 1) && tile_ready(tq) && tile_ready(tq + 1) && tile_ready(tk) &&
+          if (mbar_test_wait(&B.sdp_free[buf], ((nsb >> 1) & 1) ^ 1) && tile_ready(tq) && tile_ready(tq + 1) && tile_ready(tk) &&
               tile_ready(tk + 1)) {
             tcgen05_fence_after();
             const int kk = keys_of(S, S.j);
@@ -340,9 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
         }
         // ---- accumulate MMAs of the next block whose P / dS tiles are written
         {
-          bool ok = mbar_try_wait(B.pds_full, nblk & 1);
-          if (ok && A.i == 0 && jcount > 0) ok = mbar_try_wait(B.dkv_free, (jcount & 1) ^ 1);       // previous dK / dV drained
-          if (ok && A.i == 0 && A.j == 0 && A.k > 0) ok = mbar_try_wait(B.dq_free, (A.k & 1) ^ 1);  // previous item's dQ drained
+          bool ok = mbar_test_wait(B.pds_full, nblk & 1);
+          if (ok && A.i == 0 && jcount > 0) ok = mbar_test_wait(B.dkv_free, (jcount & 1) ^ 1);       // previous dK / dV drained
+          if (ok && A.i == 0 && A.j == 0 && A.k > 0) ok = mbar_test_wait(B.dq_free, (A.k & 1) ^ 1);  // previous item's dQ drained
           if (ok) {
             tcgen05_fence_after();
             const int i = A.i, j = A.j, nt = A.nt;
@@ -387,7 +387,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
             progress = true;
           }
         }
-        if (!progress) __nanosleep(32);
       }
     }
   } else if (warp < 2 + kGroupWarps) {
