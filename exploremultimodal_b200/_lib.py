@@ -80,6 +80,7 @@ _SIGNATURES = {
     'mome_cast_bf16': (C.c_int, [_P, _P, _L, _P]),
     'mome_gemm': (C.c_int, [C.POINTER(GemmArgs), _P]),
     'mome_attn_fwd': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, C.c_uint32, _F, _P]),
+    'mome_attn_bwd_ws_floats': (C.c_int64, [_L, _I, _I, _I]),
     'mome_attn_bwd': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, C.c_uint32, _F, _P]),
     'mome_l2norm_fwd': (C.c_int, [_P, C.c_int, _P, _P, _L, _L, _P]),
     'mome_l2norm_bwd': (C.c_int, [_P, _P, _P, _P, _L, _L, _P]),

@@ -35,15 +35,19 @@ int attn_bwd_tc_pipe(const void* qkv, const void* out, const void* dout, const i
                      void* dqkv, float* delta_ws, int64_t tokens, int num_seqs, int max_seq_len, int H, float scale, const uint32_t* drop_seed,
                      uint32_t drop_salt, float drop_p, cudaStream_t stream);
 
-// The tcgen05 backward takes the same shape window. MOME_ATTN_TC_BWD: unset = the software-pipelined kernel
-// (attention_tc_bwd_pipe.cu), 1 / 2 / 3 = the first kernel and its variants (attention_tc_bwd.cu), 0 = mma.sync.
+int attn_bwd_tc_pipe_max_seq_len();
+int64_t attn_bwd_tc_pipe_extra_ws_floats(int64_t tokens, int max_seq_len, int H);
+
+// The tcgen05 backward. MOME_ATTN_TC_BWD: unset = the software-pipelined kernel (attention_tc_bwd_pipe.cu; sequences of
+// 65 .. 1024 tokens, i.e. also VQA at 480 px), 1 / 2 / 3 = the first kernel and its variants (attention_tc_bwd.cu, up to
+// 256 tokens), 0 = mma.sync.
+static bool use_tc_bwd_pipe(int max_seq_len) {
+  const char* e = getenv("MOME_ATTN_TC_BWD");
+  return (e == nullptr || e[0] == '\0' || e[0] == 'p') && max_seq_len > 64 && max_seq_len <= attn_bwd_tc_pipe_max_seq_len();
+}
 static bool use_tc_bwd(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC_BWD");
-  return (e == nullptr || e[0] != '0') && max_seq_len > 64 && max_seq_len <= 256;
-}
-static bool use_tc_bwd_pipe() {
-  const char* e = getenv("MOME_ATTN_TC_BWD");
-  return e == nullptr || e[0] == '\0' || e[0] == 'p';
+  return e != nullptr && e[0] >= '1' && e[0] <= '3' && max_seq_len > 64 && max_seq_len <= 256;
 }
 
 // MOME_ATTN_SIMT=1 forces the CUDA-core kernels for bf16 too (cross-check in tests / debugging).
@@ -74,6 +78,11 @@ extern "C" int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc
   return attn_fwd_simt_dispatch(qkv, dtype, seq_desc, key_mask, out, lse, num_seqs, max_seq_len, num_heads, scale, s);
 }
 
+extern "C" int64_t mome_attn_bwd_ws_floats(int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads) {
+  const int64_t delta = (static_cast<int64_t>(num_seqs) * num_heads * max_seq_len + 3) & ~int64_t(3);
+  return delta + attn_bwd_tc_pipe_extra_ws_floats(tokens, max_seq_len, num_heads);
+}
+
 extern "C" int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
                              const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens, int32_t num_seqs,
                              int32_t max_seq_len, int32_t num_heads, float scale, const uint32_t* drop_seed, uint32_t drop_salt,
@@ -84,7 +93,7 @@ extern "C" int mome_attn_bwd(const void* qkv, const void* out, const void* dout,
   MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_bwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
   if (num_seqs == 0 || tokens == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == MOME_BF16 && !force_simt() && use_tc_bwd(max_seq_len) && use_tc_bwd_pipe())
+  if (dtype == MOME_BF16 && !force_simt() && use_tc_bwd_pipe(max_seq_len))
     return attn_bwd_tc_pipe(qkv, out, dout, seq_desc, key_mask, lse, dqkv, delta_ws, tokens, num_seqs, max_seq_len, num_heads, scale,
                             drop_seed, drop_salt, drop_p, s);
   if (dtype == MOME_BF16 && !force_simt() && use_tc_bwd(max_seq_len))

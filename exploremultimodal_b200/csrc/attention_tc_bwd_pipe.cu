@@ -1,23 +1,30 @@
 // K1 backward on tcgen05 / TMEM / TMA, software-pipelined (round 2). Same contract and same arithmetic as
-// attention_tc_bwd.cu (mask semantics, lse format, dropout mask function, dqkv layout); what changes is the schedule.
+// attention_tc_bwd.cu (mask semantics, lse format, dropout mask function, dqkv layout); what changes is the schedule,
+// and sequences may be longer than 256 tokens (VQA at 480 px: 941).
 //
 // ncu of the first kernel (profiles/r02_attn_bwd_ncu.md): the P / dS warps spend 22 % of their time on the P / dS
 // arithmetic and the rest waiting — for S / dP of the block (the tensor core only starts them once the previous block's
 // accumulate MMAs were issued), for dK / dV / dQ to become final so that they can drain them themselves, for the next
-// item's TMA loads (issued after the last MMA of the item), for lse / delta loads at the start of an item. Here every one
-// of these waits has something else to overlap with:
+// item's TMA loads (issued after the last MMA of the item), for lse / delta loads at the start of an item. Here:
 //
+//   * an item is (sequence, head, PAIR of 128-query tiles); it visits every 128-key block of the sequence, key block by key
+//     block, so dQ_0 / dQ_1 accumulate in TMEM over the whole item and dK_j / dV_j over the item's two query tiles;
 //   * S / dP are computed per SUB-BLOCK of 128 queries x 64 keys into a two-deep ring of TMEM buffers
 //     (2 x (64 + 64) columns); the P / dS warps copy a sub-block into registers and hand the buffer back at once,
-//     so the tensor core is always one to two sub-blocks ahead of them;
+//     so the tensor core is one to two sub-blocks ahead of them;
 //   * the accumulate MMAs (dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j) stay per 128 x 128 block, M = 128 keys;
-//     the P / dS warps keep a sub-block's results in registers and only wait for the previous block's MMAs to have
-//     finished reading the P / dS tiles at their first store;
-//   * dK / dV / dQ are drained by four extra warps, not by the P / dS warps;
-//   * Q, K, V, dO live in a ring of eight 128-row tiles with a full / empty barrier pair each. A tile is released by the
-//     last MMA that reads it, so K_0 / V_0 of the next item arrive while the second key block of this item is processed,
-//     and two 1-tile (text) items are in flight at once;
+//   * dK / dV / dQ are drained by four extra warps, not by the P / dS warps. A sequence with one query pair (<= 256
+//     tokens) stores dK_j / dV_j directly; longer ones add them (fp32 red.add) into a scratch [tokens, 2 d] that a small
+//     kernel converts afterwards — the only atomics, and only on the long-sequence path;
+//   * Q, dO live in a ring of four 128-row tiles, K, V in another ring of four, a full / empty barrier pair per tile. A tile
+//     is released by the last MMA that reads it, so the next key block (or K_0 / V_0 of the next item) arrives while this
+//     one is processed, and two 1-tile (text) items are in flight at once;
 //   * a thread fetches the next item's lse / delta while it works on this one.
+//
+// What bounds it now (MOME_ATTN_DBG event trace + tools/umma_probe.cu): with head_dim 64 every MMA has N = 64, i.e. 6 KB of
+// shared-memory operands for 32 tensor-pipe cycles; operand fetch (~64 B/clk) and the issuing thread (~90 cycles per
+// tcgen05.mma) both sit at ~95 cycles per MMA, 40 MMAs per 128 x 128 block = ~3800 cycles, next to ~3600 cycles of
+// P / dS work per block. Three issuing threads and register-deferred tile stores were tried and measured no faster.
 //
 // TMEM (512 columns): dQ_0 | dQ_1 | dK_j | dV_j (64 each) | S_0 dP_0 | S_1 dP_1 (64 each).
 // Shared memory: 8 operand tiles (128 KB), P and dS tiles (2 x 32 KB, two 64-key chunks each), 4 meta slots, barriers.
@@ -49,15 +56,16 @@ namespace {
 constexpr int kHd = 64;
 constexpr int kTile = 128;  // query tile = key block = MMA M = TMEM lanes
 constexpr int kSub = 64;    // keys of a sub-block (S / dP granularity)
-constexpr int kMaxKeys = 256;
+constexpr int kMaxKeys = 1024;
+constexpr int kMaxKeyBlocks = kMaxKeys / kTile;
 constexpr float kLog2e = 1.4426950408889634f;
 
 constexpr int kTileBytes = kTile * 128;  // 128 rows x 64 bf16
-constexpr int kSlots = 8;
+constexpr int kSlots = 8;                // 0-3: Q / dO ring, 4-7: K / V ring
 constexpr int kPOff = kSlots * kTileBytes, kSOff = kPOff + 2 * kTileBytes;  // P, dS: 2 chunks of 64 keys x [128 q x 128 B]
-constexpr int kMetaOff = kSOff + 2 * kTileBytes;                              // 4 slots x 64 B: keep words [8], seq desc [4]
-constexpr int kMetaSlots = 4;
-constexpr int kBarOff = kMetaOff + kMetaSlots * 64;
+constexpr int kMetaOff = kSOff + 2 * kTileBytes;                              // 4 slots: keep words [32], seq desc [4]
+constexpr int kMetaSlots = 4, kMetaBytes = 192;
+constexpr int kBarOff = kMetaOff + kMetaSlots * kMetaBytes;
 constexpr int kSmemBytes = kBarOff + 512 + 1024;
 constexpr int kGroupWarps = 8, kDrainWarps = 4;
 constexpr int kThreads = 64 + 32 * (kGroupWarps + kDrainWarps);
@@ -99,6 +107,9 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
+__device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct Params {
   CUtensorMap qkv32, qkv8;  // qkv as [tokens][3 d] bf16, boxes of 64 columns x 32 / 8 rows
@@ -110,15 +121,31 @@ struct Params {
   const float* lse;
   const float* delta;
   __nv_bfloat16* dqkv;
-  int H, max_seq_len, num_items;
+  float* dkv_acc;  // [tokens][2 d] fp32, zeroed: dK / dV of sequences with several query pairs (nullptr when QP == 1)
+  int H, max_seq_len, num_items, QP;  // QP: query pairs per (sequence, head) = items per (sequence, head)
   float scale;
   const uint32_t* drop_seed;
   uint32_t drop_salt, drop_thr;
 };
 
-// Tiles of an item in loading order = order of first use: K_0 V_0 Q_0 dO_0 [Q_1 dO_1] [K_1 V_1]
-__device__ __forceinline__ int tile_k(int j, int nt) { return j == 0 ? 0 : 2 + 2 * nt + 2 * (j - 1); }
-__device__ __forceinline__ int tile_q(int i) { return 2 + 2 * i; }
+// An item = (sequence, head, query pair). Geometry from the sequence length: query tiles of the pair (0: the pair lies past
+// the end of this sequence — every role skips the item), key blocks of the sequence.
+struct Geo {
+  int sh, qp, n, nqt, nkb;
+};
+__device__ __forceinline__ Geo item_geo(const Params& p, int item, int n) {
+  Geo g;
+  g.sh = item / p.QP;
+  g.qp = item - g.sh * p.QP;
+  g.n = n;
+  g.nkb = (n + kTile - 1) / kTile;
+  g.nqt = max(0, min(2, g.nkb - 2 * g.qp));
+  return g;
+}
+__device__ __forceinline__ int item_len(const Params& p, int item) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p.seq_desc + 4 * ((item / p.QP) / p.H)));
+  return v.y + v.w;
+}
 
 struct Bars {
   uint64_t* full;       // [8] producer -> MMA: tile loaded
@@ -137,6 +164,9 @@ __device__ __forceinline__ Bars make_bars(uint8_t* smem) {
   uint64_t* b = reinterpret_cast<uint64_t*>(smem + kBarOff);
   return Bars{b, b + 8, b + 16, b + 20, b + 22, b + 24, b + 25, b + 26, b + 27, b + 28, b + 29};
 }
+// ring positions: the Q / dO ring (slots 0-3) and the K / V ring (slots 4-7) count their tiles separately
+__device__ __forceinline__ uint32_t q_slot(uint32_t cq) { return cq & 3; }
+__device__ __forceinline__ uint32_t k_slot(uint32_t ck) { return 4 + (ck & 3); }
 
 // one tile of an operand: sequence-local rows [r0, r1) -> TMA boxes (32-row boxes, then 8-row boxes; a range's last box may
 // run past it into finite rows nobody reads unmasked). Returns the bytes the boxes carry.
@@ -204,46 +234,50 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------ producer
-    uint32_t cnt = 0;  // tiles loaded so far: slot = cnt & 7, fill number = cnt >> 3
-    int k = 0;
-    Seq sd_next = blockIdx.x < p.num_items ? load_seq(p.seq_desc, blockIdx.x / H) : Seq{0, 0, 0, 0};
-    for (int item = blockIdx.x; item < p.num_items; item += G, ++k) {
-      const int s = item / H, h = item - s * H;
-      const Seq sd = sd_next;
-      if (item + G < p.num_items) sd_next = load_seq(p.seq_desc, (item + G) / H);
-      const int n = sd.len0 + sd.len1;
-      const int nt = n > kTile ? 2 : 1;
-      // ---- meta: keep words of the item's keys, its descriptor (slot k & 3: the groups are at most two items behind)
-      uint32_t* meta = reinterpret_cast<uint32_t*>(smem + kMetaOff + (k & (kMetaSlots - 1)) * 64);
-      uint8_t mk[8];
-#pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) {
+    uint32_t cq = 0, ck = 0;  // tiles loaded so far into the Q / dO ring and the K / V ring (fill number = count >> 2)
+    int k = 0;                // non-empty items so far
+    for (int item = blockIdx.x; item < p.num_items; item += G) {
+      const Geo g = item_geo(p, item, item_len(p, item));
+      if (g.nqt == 0) continue;
+      const int s = g.sh / H, h = g.sh - s * H;
+      const Seq sd = load_seq(p.seq_desc, s);
+      const int n = g.n;
+      // the meta slot's previous user is item k - 4: the K / V ring slot waited for here was released by item k - 1 or
+      // k - 2, and the groups finished item k - 4 long before that
+      wait_bar(&B.empty[k_slot(ck)], ((ck >> 2) & 1) ^ 1);
+      uint32_t* meta = reinterpret_cast<uint32_t*>(smem + kMetaOff + (k & (kMetaSlots - 1)) * kMetaBytes);
+#pragma unroll 1
+      for (int j8 = 0; j8 < g.nkb * 4; ++j8) {
         const int j = j8 * 32 + lane;
-        mk[j8] = j < n ? (p.key_mask == nullptr ? uint8_t(1) : __ldg(p.key_mask + seq_row(sd, j))) : uint8_t(0);
-      }
-      // the slot's previous user is item k - 4; item k - 2 has released the first ring slot this item needs before the
-      // loads below can start, and the groups finished item k - 4 long before that
-      wait_bar(&B.empty[cnt & 7], ((cnt >> 3) & 1) ^ 1);
-#pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) {
-        const uint32_t w = __ballot_sync(0xffffffffu, mk[j8] != 0);
+        const bool keep = j < n && (p.key_mask == nullptr || __ldg(p.key_mask + seq_row(sd, j)) != 0);
+        const uint32_t w = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) meta[j8] = w;
       }
       if (lane == 0) {
-        meta[8] = sd.start0; meta[9] = sd.len0; meta[10] = sd.start1; meta[11] = sd.len1;
+        meta[32] = sd.start0; meta[33] = sd.len0; meta[34] = sd.start1; meta[35] = sd.len1;
         mbar_arrive(&B.meta_full[k & (kMetaSlots - 1)]);
       }
+      ++k;
       const bool boxes_ok = sd.len1 == 0 || (sd.len0 & 7) == 0;
-      const int ntiles = 4 * nt;
+      // loading order = order of first use: K_0 V_0 | Q_0 dO_0 [Q_1 dO_1] | K_1 V_1 | K_2 V_2 ...
+      const int ntiles = 2 * g.nqt + 2 * g.nkb;
 #pragma unroll 1
-      for (int t = 0; t < ntiles; ++t, ++cnt) {
-        // t -> (operand, row tile): 0 K_0, 1 V_0, 2 Q_0, 3 dO_0, 4 Q_1, 5 dO_1, 6 K_1, 7 V_1
-        const int op = (t == 0 || t == 6) ? 1 : (t == 1 || t == 7) ? 2 : (t & 1) ? 3 : 0;  // 0 Q, 1 K, 2 V, 3 dO
-        const int rt = (t < 4) ? 0 : 1;
-        const int slot = cnt & 7;
+      for (int t = 0; t < ntiles; ++t) {
+        int op, rt;  // operand 0 Q, 1 K, 2 V, 3 dO; 128-row tile of the sequence
+        if (t < 2) {
+          op = 1 + t; rt = 0;
+        } else if (t < 2 + 2 * g.nqt) {
+          op = (t & 1) ? 3 : 0; rt = 2 * g.qp + ((t - 2) >> 1);
+        } else {
+          op = 1 + (t & 1); rt = 1 + ((t - 2 - 2 * g.nqt) >> 1);
+        }
+        const bool is_q = op == 0 || op == 3;
+        const uint32_t cnt = is_q ? cq : ck;
+        const uint32_t slot = is_q ? q_slot(cnt) : k_slot(cnt);
+        if (is_q) ++cq; else ++ck;
         uint8_t* dst = smem + slot * kTileBytes;
         const int r0 = rt * kTile, r1 = min(n, r0 + kTile);
-        wait_bar(&B.empty[slot], ((cnt >> 3) & 1) ^ 1);
+        wait_bar(&B.empty[slot], ((cnt >> 2) & 1) ^ 1);
         __syncwarp();
         if (boxes_ok) {
           if (elect_one()) {
@@ -278,44 +312,49 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
     // ------------------------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t sP = smem_u32(smem + kPOff), sS = smem_u32(smem + kSOff), sR = smem_u32(smem);
-      const int first = blockIdx.x;
       struct Cur {
-        int k, n, nt, j, i, c;
-        uint32_t tb;  // tiles of the items before this one
+        int item, k, n, nqt, nkb, j, i, c;
+        uint32_t cq, ck;  // ring counts at the start of the item
       };
-      auto item_n = [&](int k) {
-        const int item = first + k * G;
-        if (item >= p.num_items) return 0;
-        const int4 v = __ldg(reinterpret_cast<const int4*>(p.seq_desc + 4 * (item / H)));
-        return v.y + v.w;
+      // move to the next non-empty item at or after `item` (n = 0: past the end)
+      auto seek = [&](Cur& c, int item) {
+        for (; item < p.num_items; item += G) {
+          const Geo g = item_geo(p, item, item_len(p, item));
+          if (g.nqt > 0) {
+            c.item = item; c.n = g.n; c.nqt = g.nqt; c.nkb = g.nkb;
+            c.j = c.i = c.c = 0;
+            return;
+          }
+        }
+        c.item = item; c.n = 0; c.nqt = c.nkb = 0;
       };
       auto next_item = [&](Cur& c) {
-        c.tb += 4 * c.nt;
+        c.cq += 2 * c.nqt;
+        c.ck += 2 * c.nkb;
         ++c.k;
-        c.n = item_n(c.k);
-        c.nt = c.n > kTile ? 2 : 1;
-        c.j = c.i = c.c = 0;
+        seek(c, c.item + G);
       };
       auto keys_of = [](const Cur& c, int j) { return min(kTile, pad16(c.n - j * kTile)); };
-      auto slot_addr = [&](uint32_t cnt) { return sR + (cnt & 7) * kTileBytes; };
-      auto tile_ready = [&](uint32_t cnt) { return mbar_test_wait(&B.full[cnt & 7], (cnt >> 3) & 1); };
-      Cur S{0, item_n(0), 0, 0, 0, 0, 0};
-      S.nt = S.n > kTile ? 2 : 1;
+      auto q_addr = [&](uint32_t cnt) { return sR + q_slot(cnt) * kTileBytes; };
+      auto k_addr = [&](uint32_t cnt) { return sR + k_slot(cnt) * kTileBytes; };
+      auto q_ready = [&](uint32_t cnt) { return mbar_test_wait(&B.full[q_slot(cnt)], (cnt >> 2) & 1); };
+      auto k_ready = [&](uint32_t cnt) { return mbar_test_wait(&B.full[k_slot(cnt)], (cnt >> 2) & 1); };
+      Cur S;
+      S.k = 0; S.cq = S.ck = 0;
+      seek(S, blockIdx.x);
       Cur A = S;
       uint32_t nsb = 0, nblk = 0, jcount = 0;
       while (A.n > 0) {
-        bool progress = false;
         // ---- S = Q_i K_j^T, dP = dO_i V_j^T of the next sub-block, as soon as its TMEM buffer and its tiles are there
         if (S.n > 0) {
           const uint32_t buf = nsb & 1;
-          const uint32_t tq = S.tb + tile_q(S.i), tk = S.tb + tile_k(S.j, S.nt);
-          if (mbar_test_wait(&B.sdp_free[buf], ((nsb >> 1) & 1) ^ 1) && tile_ready(tq) && tile_ready(tq + 1) && tile_ready(tk) &&
-              tile_ready(tk + 1)) {
+          const uint32_t tq = S.cq + 2 * S.i, tk = S.ck + 2 * S.j;
+          if (mbar_test_wait(&B.sdp_free[buf], ((nsb >> 1) & 1) ^ 1) && q_ready(tq) && q_ready(tq + 1) && k_ready(tk) && k_ready(tk + 1)) {
             tcgen05_fence_after();
             const int kk = keys_of(S, S.j);
             const int ncols = min(kSub, kk - S.c * kSub);
             const uint32_t idesc = umma_idesc_bf16(kTile, ncols, false, false);
-            const uint32_t qa = slot_addr(tq), ga = slot_addr(tq + 1), ka = slot_addr(tk) + S.c * (kSub * 128), va = slot_addr(tk + 1) + S.c * (kSub * 128);
+            const uint32_t qa = q_addr(tq), ga = q_addr(tq + 1), ka = k_addr(tk) + S.c * (kSub * 128), va = k_addr(tk + 1) + S.c * (kSub * 128);
             const uint32_t ts = tmem_base + kColSdp + buf * 128;
 #pragma unroll
             for (int c = 0; c < kHd / 16; ++c)
@@ -330,12 +369,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
               S.c = 1;
             } else {
               S.c = 0;
-              if (++S.i == S.nt) {
+              if (++S.i == S.nqt) {
                 S.i = 0;
-                if (++S.j == S.nt) next_item(S);
+                if (++S.j == S.nkb) next_item(S);
               }
             }
-            progress = true;
           }
         }
         // ---- accumulate MMAs of the next block whose P / dS tiles are written
@@ -345,11 +383,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
           if (ok && A.i == 0 && A.j == 0 && A.k > 0) ok = mbar_test_wait(B.dq_free, (A.k & 1) ^ 1);  // previous item's dQ drained
           if (ok) {
             tcgen05_fence_after();
-            const int i = A.i, j = A.j, nt = A.nt;
+            const int i = A.i, j = A.j;
             const int kk = keys_of(A, j);
-            const int kq = min(kTile, pad16(A.n - i * kTile));
-            const uint32_t tq = A.tb + tile_q(i), tk = A.tb + tile_k(j, nt);
-            const uint32_t qa = slot_addr(tq), ga = slot_addr(tq + 1), ka = slot_addr(tk);
+            const int kq = min(kTile, pad16(A.n - (2 * (A.item % p.QP) + i) * kTile));
+            const uint32_t tq = A.cq + 2 * i, tk = A.ck + 2 * j;
+            const uint32_t qa = q_addr(tq), ga = q_addr(tq + 1), ka = k_addr(tk);
             // dV_j += P^T dO_i, dK_j += dS^T Q_i: A = [q][keys] tile read MN-major (M = keys), K = query rows
             const uint32_t idesc_t = umma_idesc_bf16(kTile, kHd, true, true);
             const int steps_q = kq >> 4;
@@ -367,24 +405,23 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
                         umma_smem_desc(ka + c * 2048, 8192, 1024), idesc_q, (j > 0 || c > 0) ? 1u : 0u);
             umma_commit(B.pds_free);
             ++nblk;
-            if (i == nt - 1) {  // key block done: dK_j / dV_j final, K_j / V_j no longer needed
+            if (i == A.nqt - 1) {  // key block done: dK_j / dV_j final, K_j / V_j no longer needed
               umma_commit(B.dkv_full);
               ++jcount;
-              umma_commit(&B.empty[tk & 7]);
-              umma_commit(&B.empty[(tk + 1) & 7]);
+              umma_commit(&B.empty[k_slot(tk)]);
+              umma_commit(&B.empty[k_slot(tk + 1)]);
             }
-            if (j == nt - 1) {  // last key block: Q_i / dO_i no longer needed
-              umma_commit(&B.empty[tq & 7]);
-              umma_commit(&B.empty[(tq + 1) & 7]);
+            if (j == A.nkb - 1) {  // last key block: Q_i / dO_i no longer needed
+              umma_commit(&B.empty[q_slot(tq)]);
+              umma_commit(&B.empty[q_slot(tq + 1)]);
             }
-            if (++A.i == nt) {
+            if (++A.i == A.nqt) {
               A.i = 0;
-              if (++A.j == nt) {
+              if (++A.j == A.nkb) {
                 umma_commit(B.dq_full);
                 next_item(A);
               }
             }
-            progress = true;
           }
         }
       }
@@ -402,41 +439,44 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
     const int cb = part * 4, sw = row & 7;
     uint32_t nsb = 0, nblk = 0;
     int k = 0;
-    // lse (log2 domain; +inf for absent rows => P = 0) and delta of this thread's row in both query tiles, fetched one item ahead
+    // lse (log2 domain; +inf for absent rows => P = 0) and delta of this thread's row in both query tiles, fetched one item
+    // ahead. Rows are clamped into the (sequence, head)'s own max_seq_len slots, so the loads do not wait for the sequence
+    // length; absent rows are recognised when the values are used.
     float Ln[2], Dn[2];
-    // rows are clamped into the (sequence, head)'s own max_seq_len slots, so the loads do not wait for the sequence length;
-    // absent rows are recognised when the values are used
-    const int qc0 = min(row, p.max_seq_len - 1), qc1 = min(kTile + row, p.max_seq_len - 1);
     auto fetch = [&](int item, float (&L)[2], float (&D)[2]) {
       if (item < p.num_items) {
-        const long long stat0 = static_cast<long long>(item) * p.max_seq_len;  // item = s H + h
-        L[0] = __ldg(p.lse + stat0 + qc0);
-        L[1] = __ldg(p.lse + stat0 + qc1);
-        D[0] = __ldg(p.delta + stat0 + qc0);
-        D[1] = __ldg(p.delta + stat0 + qc1);
+        const int sh = item / p.QP, qp = item - sh * p.QP;
+        const long long stat0 = static_cast<long long>(sh) * p.max_seq_len;  // sh = s H + h
+        const int q0 = min(2 * qp * kTile + row, p.max_seq_len - 1), q1 = min((2 * qp + 1) * kTile + row, p.max_seq_len - 1);
+        L[0] = __ldg(p.lse + stat0 + q0);
+        L[1] = __ldg(p.lse + stat0 + q1);
+        D[0] = __ldg(p.delta + stat0 + q0);
+        D[1] = __ldg(p.delta + stat0 + q1);
       }
     };
     fetch(blockIdx.x, Ln, Dn);
-    for (int item = blockIdx.x; item < p.num_items; item += G, ++k) {
-      const int s = item / H, h = item - s * H;
-      wait_bar(&B.meta_full[k & (kMetaSlots - 1)], (k >> 2) & 1);
-      const uint32_t meta = smem_u32(smem + kMetaOff + (k & (kMetaSlots - 1)) * 64);
-      const int n = static_cast<int>(lds_u32(meta + 36) + lds_u32(meta + 44));
-      const int nt = n > kTile ? 2 : 1;
+    for (int item = blockIdx.x; item < p.num_items; item += G) {
+      const Geo g = item_geo(p, item, item_len(p, item));
       float Lr[2], Dr[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        Lr[i] = i * kTile + row < n ? Ln[i] * kLog2e : INFINITY;
-        Dr[i] = i * kTile + row < n ? Dn[i] : 0.f;
+        Lr[i] = (2 * g.qp + i) * kTile + row < g.n ? Ln[i] * kLog2e : INFINITY;
+        Dr[i] = (2 * g.qp + i) * kTile + row < g.n ? Dn[i] : 0.f;
       }
       fetch(item + G, Ln, Dn);
-      for (int j = 0; j < nt; ++j) {
+      if (g.nqt == 0) continue;
+      const int s = g.sh / H, h = g.sh - s * H;
+      const int n = g.n;
+      wait_bar(&B.meta_full[k & (kMetaSlots - 1)], (k >> 2) & 1);
+      const uint32_t meta = smem_u32(smem + kMetaOff + (k & (kMetaSlots - 1)) * kMetaBytes);
+      ++k;
+      for (int j = 0; j < g.nkb; ++j) {
         const int kk = min(kTile, pad16(n - j * kTile));
         const int nsub = kk > kSub ? 2 : 1;
-        for (int i = 0; i < nt; ++i, ++nblk) {
-          const int q = i * kTile + row;
+        for (int i = 0; i < g.nqt; ++i, ++nblk) {
+          const int q = (2 * g.qp + i) * kTile + row;
           const float L = Lr[i], D = Dr[i];
-          const bool warp_live = i * kTile + quarter * 32 < n;  // some row of this warp is a real query
+          const bool warp_live = (2 * g.qp + i) * kTile + quarter * 32 < n;  // some row of this warp is a real query
           for (int c = 0; c < nsub; ++c, ++nsb) {
             const uint32_t buf = nsb & 1;
             const int key0 = c * kSub + part * 32;  // first of this thread's 32 keys inside the block
@@ -516,68 +556,101 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_pipe_kernel(const __g
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const long long ld3 = 3LL * d;
     const float scale = p.scale;
+    const bool atomic_kv = p.dkv_acc != nullptr;
     uint32_t jcount = 0;
     int k = 0;
-    // 64 fp32 accumulator columns of this thread's lane -> 64 bf16 (x mul) = one 128-byte row segment
-    auto load64 = [&](uint32_t col, float mul, uint4 (&o)[8]) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+    // 32 fp32 accumulator columns of this thread's lane -> 32 bf16 (x mul) = 64 bytes of a row
+    auto drain32_store = [&](uint32_t col, float mul, __nv_bfloat16* dst, bool live, bool valid) {
+      if (live) {  // warp-uniform
         uint32_t a[32];
-        tmem_ld_32x32(trow + col + hf * 32, a);
+        tmem_ld_32x32(trow + col, a);
         tmem_ld_wait();
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          o[hf * 4 + e] = make_uint4(pack_bf16(__uint_as_float(a[8 * e]) * mul, __uint_as_float(a[8 * e + 1]) * mul),
-                                     pack_bf16(__uint_as_float(a[8 * e + 2]) * mul, __uint_as_float(a[8 * e + 3]) * mul),
-                                     pack_bf16(__uint_as_float(a[8 * e + 4]) * mul, __uint_as_float(a[8 * e + 5]) * mul),
-                                     pack_bf16(__uint_as_float(a[8 * e + 6]) * mul, __uint_as_float(a[8 * e + 7]) * mul));
+          for (int e = 0; e < 4; ++e)
+            d4[e] = make_uint4(pack_bf16(__uint_as_float(a[8 * e]) * mul, __uint_as_float(a[8 * e + 1]) * mul),
+                               pack_bf16(__uint_as_float(a[8 * e + 2]) * mul, __uint_as_float(a[8 * e + 3]) * mul),
+                               pack_bf16(__uint_as_float(a[8 * e + 4]) * mul, __uint_as_float(a[8 * e + 5]) * mul),
+                               pack_bf16(__uint_as_float(a[8 * e + 6]) * mul, __uint_as_float(a[8 * e + 7]) * mul));
+        }
       }
     };
-    auto store64 = [&](__nv_bfloat16* dst, const uint4 (&o)[8]) {
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+    auto drain32_add = [&](uint32_t col, float* dst, bool live, bool valid) {
+      if (live) {
+        uint32_t a[32];
+        tmem_ld_32x32(trow + col, a);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) d4[e] = o[e];
+          for (int e = 0; e < 8; ++e)
+            red_add_v4(dst + 4 * e, __uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]), __uint_as_float(a[4 * e + 2]),
+                       __uint_as_float(a[4 * e + 3]));
+        }
+      }
     };
-    for (int item = blockIdx.x; item < p.num_items; item += G, ++k) {
-      const int s = item / H, h = item - s * H;
+    for (int item = blockIdx.x; item < p.num_items; item += G) {
+      const Geo g = item_geo(p, item, item_len(p, item));
+      if (g.nqt == 0) continue;
+      const int s = g.sh / H, h = g.sh - s * H;
       const Seq sd = load_seq(p.seq_desc, s);
-      const int n = sd.len0 + sd.len1;
-      const int nt = n > kTile ? 2 : 1;
-      for (int j = 0; j < nt; ++j, ++jcount) {
+      const int n = g.n;
+      for (int j = 0; j < g.nkb; ++j, ++jcount) {
         const int key = j * kTile + row;
-        const bool warp_live = j * kTile + quarter * 32 < n;
+        const bool live = j * kTile + quarter * 32 < n, valid = key < n;
+        const long long grow = seq_row(sd, min(key, n - 1));
         wait_bar(B.dkv_full, jcount & 1);
         __syncwarp();
         tcgen05_fence_after();
-        __nv_bfloat16* base = p.dqkv + seq_row(sd, min(key, n - 1)) * ld3 + h * kHd;
-        {
-          uint4 o[8];
-          if (warp_live) load64(kColDK, scale, o);
-          if (key < n) store64(base + d, o);
-          if (warp_live) load64(kColDV, 1.f, o);
-          tcgen05_fence_before();
-          mbar_arrive(B.dkv_free);
-          if (key < n) store64(base + 2 * d, o);
+        if (!atomic_kv) {
+          __nv_bfloat16* base = p.dqkv + grow * ld3 + h * kHd;
+          drain32_store(kColDK, scale, base + d, live, valid);
+          drain32_store(kColDK + 32, scale, base + d + 32, live, valid);
+          drain32_store(kColDV, 1.f, base + 2 * d, live, valid);
+          drain32_store(kColDV + 32, 1.f, base + 2 * d + 32, live, valid);
+        } else {  // several query pairs add into the same rows (the scale is applied by the conversion kernel)
+          float* base = p.dkv_acc + grow * (2LL * d) + h * kHd;
+          drain32_add(kColDK, base, live, valid);
+          drain32_add(kColDK + 32, base + 32, live, valid);
+          drain32_add(kColDV, base + d, live, valid);
+          drain32_add(kColDV + 32, base + d + 32, live, valid);
         }
+        tcgen05_fence_before();
+        mbar_arrive(B.dkv_free);
       }
       wait_bar(B.dq_full, k & 1);
+      ++k;
       __syncwarp();
       tcgen05_fence_after();
-      {
-        uint4 o[8];
-        const bool live0 = quarter * 32 < n, live1 = kTile + quarter * 32 < n;
-        if (live0) load64(kColDQ, scale, o);
-        if (row < n) store64(p.dqkv + seq_row(sd, row) * ld3 + h * kHd, o);
-        if (live1) load64(kColDQ + 64, scale, o);
-        tcgen05_fence_before();
-        mbar_arrive(B.dq_free);
-        if (kTile + row < n) store64(p.dqkv + seq_row(sd, kTile + row) * ld3 + h * kHd, o);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = (2 * g.qp + i) * kTile + row;
+        const bool live = i < g.nqt && (2 * g.qp + i) * kTile + quarter * 32 < n, valid = i < g.nqt && q < n;
+        __nv_bfloat16* base = p.dqkv + seq_row(sd, min(q, n - 1)) * ld3 + h * kHd;
+        drain32_store(kColDQ + i * 64, scale, base, live, valid);
+        drain32_store(kColDQ + i * 64 + 32, scale, base + 32, live, valid);
       }
+      tcgen05_fence_before();
+      mbar_arrive(B.dq_free);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dK / dV of the long-sequence path: scratch [tokens][2 d] fp32 -> the k and v thirds of dqkv (k scaled)
+__global__ void __launch_bounds__(256) attn_dkv_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long tokens,
+                                                               int d, float scale) {
+  const long long per_row = 2LL * d / 8;  // 8 elements per thread
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= tokens * per_row) return;
+  const long long row = idx / per_row;
+  const int c = static_cast<int>(idx - row * per_row) * 8;
+  const float mul = c < d ? scale : 1.f;
+  const float4 a = *reinterpret_cast<const float4*>(acc + row * 2LL * d + c), b = *reinterpret_cast<const float4*>(acc + row * 2LL * d + c + 4);
+  *reinterpret_cast<uint4*>(dqkv + row * 3LL * d + d + c) =
+      make_uint4(pack_bf16(a.x * mul, a.y * mul), pack_bf16(a.z * mul, a.w * mul), pack_bf16(b.x * mul, b.y * mul), pack_bf16(b.z * mul, b.w * mul));
 }
 
 template <typename K>
@@ -591,6 +664,13 @@ int opt_in(K kern, int bytes, const char* what) {
 }
 
 }  // namespace
+
+int attn_bwd_tc_pipe_max_seq_len() { return kMaxKeys; }
+
+// floats of workspace behind the num_seqs * H * max_seq_len delta values: the dK / dV scratch of the long-sequence path
+int64_t attn_bwd_tc_pipe_extra_ws_floats(int64_t tokens, int max_seq_len, int H) {
+  return max_seq_len > 2 * kTile ? tokens * 2 * H * kHd : 0;
+}
 
 int attn_bwd_tc_pipe(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask, const float* lse,
                      void* dqkv, float* delta_ws, int64_t tokens, int num_seqs, int max_seq_len, int H, float scale, const uint32_t* drop_seed,
@@ -619,11 +699,22 @@ int attn_bwd_tc_pipe(const void* qkv, const void* out, const void* dout, const i
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.H = H;
   p.max_seq_len = max_seq_len;
-  p.num_items = num_seqs * H;
+  p.QP = ((max_seq_len + kTile - 1) / kTile + 1) / 2;
+  p.num_items = num_seqs * H * p.QP;
   p.scale = scale;
   p.drop_seed = drop_seed;
   p.drop_salt = drop_salt;
   p.drop_thr = drop_threshold(drop_p);
+  p.dkv_acc = nullptr;
+  if (p.QP > 1) {  // workspace layout: delta [num_seqs H max_seq_len] | dK / dV scratch [tokens][2 d]
+    const int64_t delta_floats = (static_cast<int64_t>(num_seqs) * H * max_seq_len + 3) & ~int64_t(3);
+    p.dkv_acc = delta_ws + delta_floats;
+    cudaError_t e = cudaMemsetAsync(p.dkv_acc, 0, static_cast<size_t>(tokens) * 2 * d * sizeof(float), stream);
+    if (e != cudaSuccess) {
+      set_error("attn_bwd_tc_pipe: cudaMemsetAsync: %s", cudaGetErrorString(e));
+      return MOME_ERR_CUDA;
+    }
+  }
   rc = attn_delta_launch(out, dout, seq_desc, delta_ws, H, max_seq_len, num_seqs, stream);
   if (rc != MOME_OK) return rc;
   const int grid = std::min(p.num_items, sm_count());
@@ -631,7 +722,11 @@ int attn_bwd_tc_pipe(const void* qkv, const void* out, const void* dout, const i
     attn_bwd_tc_pipe_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
   else
     attn_bwd_tc_pipe_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  return check_launch("attn_bwd_tc_pipe");
+  rc = check_launch("attn_bwd_tc_pipe");
+  if (rc != MOME_OK || p.QP == 1) return rc;
+  const long long work = tokens * (2 * d / 8);
+  attn_dkv_convert_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(p.dkv_acc, p.dqkv, tokens, static_cast<int>(d), scale);
+  return check_launch("attn_dkv_convert");
 }
 
 }  // namespace mome

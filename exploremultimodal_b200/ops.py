@@ -160,9 +160,16 @@ def attn_fwd(qkv, lay, key_mask, num_heads, scale, drop=None):
     return out, lse
 
 
+def attn_bwd_ws(tokens, lay, num_heads, device):
+    """Scratch of mome_attn_bwd: rowsum(dO o O) per (sequence, head, query) and, for sequences longer than 256 tokens,
+    the fp32 dK / dV accumulators of the tcgen05 backward (mome.h: mome_attn_bwd_ws_floats)."""
+    n = L.lib().mome_attn_bwd_ws_floats(tokens, lay.num_seqs, lay.max_seq_len, num_heads)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
 def attn_bwd(qkv, out, dout, lay, key_mask, lse, num_heads, scale, drop=None):
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty_like(lse)
+    delta = attn_bwd_ws(qkv.shape[0], lay, num_heads, qkv.device)
     L.check(L.lib().mome_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), L.dtype_code(qkv),
                                   lay.seq_desc.data_ptr(), L.ptr(key_mask), lse.data_ptr(), dqkv.data_ptr(),
                                   delta.data_ptr(), qkv.shape[0], lay.num_seqs, lay.max_seq_len, num_heads, scale,
@@ -332,7 +339,7 @@ def block_backward(dx2, lay, key_mask, p, saved, targets=None):
     s_dz = torch.empty(tokens, hid, **act)
     s_dqkv = torch.empty(tokens, 3 * d, **act)
     s_dx1 = torch.empty_like(x)
-    s_delta = torch.empty_like(saved[6])
+    s_delta = attn_bwd_ws(tokens, lay, p.num_heads, dev)
     a.s_dbr2, a.s_dh2, a.s_dbr1, a.s_do, a.s_dh = (s_d[i].data_ptr() for i in range(5))
     a.s_dz, a.s_dqkv, a.s_dx1, a.s_delta = s_dz.data_ptr(), s_dqkv.data_ptr(), s_dx1.data_ptr(), s_delta.data_ptr()
     ws = reduce_ws(dev)

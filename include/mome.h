@@ -157,7 +157,10 @@ int mome_gemm(const MomeGemmArgs* args, void* stream);
 int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc, const uint8_t* key_mask, void* out,
                   float* lse, int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads,
                   float scale, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream);
-/* dqkv gets every element of its [tokens, 3*d] rows written. */
+/* dqkv gets every element of its [tokens, 3*d] rows written. delta_ws: scratch of mome_attn_bwd_ws_floats(...) floats
+ * (rowsum(dO o O) per (sequence, head, query); for sequences longer than 256 tokens also the fp32 dK / dV accumulators
+ * the query-tile pairs of a sequence add into). */
+int64_t mome_attn_bwd_ws_floats(int64_t tokens, int32_t num_seqs, int32_t max_seq_len, int32_t num_heads);
 int mome_attn_bwd(const void* qkv, const void* out, const void* dout, int dtype, const int32_t* seq_desc,
                   const uint8_t* key_mask, const float* lse, void* dqkv, float* delta_ws, int64_t tokens,
                   int32_t num_seqs, int32_t max_seq_len, int32_t num_heads, float scale, const uint32_t* drop_seed,

@@ -386,7 +386,7 @@ def test_attention_tcgen05_forward_matches_mma_sync(drop, mask_kind, monkeypatch
 
 
 @pytest.mark.parametrize('drop', [False, True])
-@pytest.mark.parametrize('layout', ['split', 'fused', 'gather', 'ragged'])
+@pytest.mark.parametrize('layout', ['split', 'fused', 'gather', 'ragged', 'long', 'long_gather'])
 def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatch):
     """The software-pipelined tcgen05 backward with several items per CTA (the operand-tile ring wraps, 1-tile and 2-tile
     items alternate, TMEM buffers and barriers go through many phases) against the mma.sync pair: same contract, same
@@ -403,6 +403,10 @@ def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatc
         n_seq = 48
         if layout == 'gather':
             lens = [(13, 100 + (i % 5) * 20) for i in range(n_seq)]
+        elif layout == 'long':        # VQA at 480 px and other lengths above 256: several query pairs per sequence
+            lens = [(40, 901), (40, 577), (40, 217), (8, 0), (40, 700), (40, 984), (16, 1), (40, 345), (40, 901)]
+        elif layout == 'long_gather':
+            lens = [(13, 901), (27, 500), (40, 901), (5, 260)]
         else:
             lens = [(int(a), int(b)) for a, b in zip(torch.randint(1, 41, (n_seq,), generator=g) // 8 * 8 + 8,
                                                      torch.randint(0, 209, (n_seq,), generator=g))]
@@ -415,7 +419,10 @@ def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatc
         tokens = t1
         desc = torch.tensor(seqs, dtype=torch.int32, device=_dev())
         lay = ops.PackedLayout(tokens, [(0, tokens, 'vl')], desc, len(seqs), max(a + b for a, b in lens))
-    assert 64 < lay.max_seq_len <= 256 and lay.num_seqs * H > 3 * 148
+    if layout.startswith('long'):
+        assert 256 < lay.max_seq_len <= 1024
+    else:
+        assert 64 < lay.max_seq_len <= 256 and lay.num_seqs * H > 3 * 148
     qkv = _rand(lay.tokens, 3 * 64 * H, dtype=torch.bfloat16, seed=21)
     dout = _rand(lay.tokens, 64 * H, dtype=torch.bfloat16, seed=22)
     mask = (torch.rand(lay.tokens, generator=g) > 0.15).to(torch.uint8)
@@ -437,9 +444,12 @@ def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatc
     d = 64 * H
     for name, sl in (('dq', slice(0, d)), ('dk', slice(d, 2 * d)), ('dv', slice(2 * d, 3 * d))):
         assert rel_err(grads['p'][valid][:, sl], grads['0'][valid][:, sl]) < BF16_TOL * 2, name
-    # repeatable: no atomics, no dependence on the schedule
     again = ops.attn_bwd(qkv, out, dout, lay, mask, lse, H, 0.125, dr)
-    assert torch.equal(again[valid], grads['p'][valid])
+    if layout.startswith('long'):   # dK / dV of the query pairs of a sequence meet in fp32 atomics: order-dependent rounding only
+        assert rel_err(again[valid], grads['p'][valid]) < 1e-3
+        assert torch.equal(again[valid][:, :d], grads['p'][valid][:, :d])   # dQ has a single writer
+    else:                           # repeatable: no atomics, no dependence on the schedule
+        assert torch.equal(again[valid], grads['p'][valid])
 
 
 def test_attention_no_mask_pointer():

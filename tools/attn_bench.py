@@ -41,6 +41,7 @@ def main():
                     help='MOME_ATTN_TC_BWD value for the second variant (p: software-pipelined tcgen05 backward = the library default, 1: first tcgen05 kernel, 2: + EARLY_S scheduling, 3: 16 P / dS warps); default: mma.sync backward in both')
     ap.add_argument('--check', action='store_true', help='exit 1 if the two variants disagree (used by bench.py as a pre-flight check)')
     ap.add_argument('--device', type=int, default=0)
+    ap.add_argument('--long', type=int, nargs='?', const=32, default=0, help='run the long-sequence layouts (40 + 901 / 40 + 577 tokens) over this many sequences instead')
     ap.add_argument('--only', default='', help='substring of the layout name to run')
     a = ap.parse_args()
     B, H, T, P = a.batch, a.heads, 40, 197
@@ -50,6 +51,8 @@ def main():
     bad = []
     layouts = [('fused 40+197', ops.fused_layout(B, T, P, dev)), ('split 40 / 197', ops.split_layout(B, T, P, dev)),
                ('image 197', ops.single_layout(B, P, 'v', dev)), ('text 40', ops.single_layout(B, T, 'l', dev))]
+    if a.long:  # VQA at 480 px (BASELINE configs[3]): 40 text + 901 image tokens, 32 sequences per GPU
+        layouts = [('vqa 40+901', ops.fused_layout(a.long, T, 901, dev)), ('384px 40+577', ops.fused_layout(a.long, T, 577, dev))]
     seed = torch.tensor([1234], dtype=torch.int32, device=dev)
     for name, lay in layouts:
         if a.only not in name:
@@ -61,7 +64,7 @@ def main():
             mask = (torch.rand(lay.tokens, generator=g, device=dev) > 0.1).to(torch.uint8)
         else:
             mask = torch.ones(lay.tokens, dtype=torch.uint8, device=dev)
-            if a.mask == 'pad' and name != 'image 197':  # text rows come first in every layout that has text
+            if a.mask == 'pad' and name != 'image 197' and not a.long:  # text rows come first in every layout that has text
                 lens = torch.randint(8, T + 1, (B,), generator=g, device=dev)
                 mask[:B * T] = (torch.arange(T, device=dev)[None, :] < lens[:, None]).reshape(-1).to(torch.uint8)
         for drop in (None, (seed, 7, a.drop)):
