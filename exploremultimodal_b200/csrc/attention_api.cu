@@ -22,6 +22,14 @@ int attn_fwd_tc(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mas
 // The tcgen05 forward (attention_tc.cu) takes the layouts whose sequences fit one MMA (max_seq_len <= 256) and are
 // long enough to fill its 128-row tiles; shorter ones (text-only passes) and longer ones (VQA at 480 px) stay on
 // the mma.sync kernels. MOME_ATTN_TC=0 turns it off (read per call: the tests compare the two paths).
+int attn_fwd_tc_long(const void* qkv, const int32_t* seq_desc, const uint8_t* key_mask, void* out, float* lse, int64_t tokens, int num_seqs,
+                     int max_seq_len, int H, float scale, const uint32_t* drop_seed, uint32_t drop_salt, float drop_p, cudaStream_t stream);
+int attn_fwd_tc_long_max_seq_len();
+// longer sequences (VQA at 480 / 384 px): the key-blocked tcgen05 forward with an online softmax (attention_tc_long.cu)
+static bool use_tc_long(int max_seq_len) {
+  const char* e = getenv("MOME_ATTN_TC");
+  return (e == nullptr || e[0] != '0') && max_seq_len > 256 && max_seq_len <= attn_fwd_tc_long_max_seq_len();
+}
 static bool use_tc(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC");
   return (e == nullptr || e[0] != '0') && max_seq_len > 64 && max_seq_len <= 256;
@@ -71,6 +79,8 @@ extern "C" int mome_attn_fwd(const void* qkv, int dtype, const int32_t* seq_desc
   MOME_REQUIRE(num_heads > 0 && max_seq_len > 0 && tokens >= 0, "attn_fwd: bad shape heads=%d max_seq_len=%d", num_heads, max_seq_len);
   if (num_seqs == 0 || tokens == 0) return MOME_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MOME_BF16 && !force_simt() && use_tc_long(max_seq_len))
+    return attn_fwd_tc_long(qkv, seq_desc, key_mask, out, lse, tokens, num_seqs, max_seq_len, num_heads, scale, drop_seed, drop_salt, drop_p, s);
   if (dtype == MOME_BF16 && !force_simt() && use_tc(max_seq_len))
     return attn_fwd_tc(qkv, seq_desc, key_mask, out, lse, tokens, num_seqs, max_seq_len, num_heads, scale, drop_seed, drop_salt, drop_p, s);
   if (dtype == MOME_BF16 && !force_simt())

@@ -452,6 +452,53 @@ def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatc
         assert torch.equal(again[valid], grads['p'][valid])
 
 
+def _long_layout(ops, kind):
+    lens = {'long': [(40, 901), (40, 577), (40, 217), (8, 0), (40, 700), (40, 984), (16, 1), (40, 345), (40, 901)],
+            'long_gather': [(13, 901), (27, 500), (40, 901), (5, 260)],
+            'vqa': [(40, 901)] * 14}[kind]
+    seqs, t0, t1 = [], 0, sum(a for a, _ in lens)
+    for a, b in lens:
+        seqs.append((t0, a, t1 if b > 0 else 0, b))
+        t0 += a
+        t1 += b
+    desc = torch.tensor(seqs, dtype=torch.int32, device=_dev())
+    return ops.PackedLayout(t1, [(0, t1, 'vl')], desc, len(seqs), max(a + b for a, b in lens))
+
+
+@pytest.mark.parametrize('drop', [False, True])
+@pytest.mark.parametrize('layout', ['long', 'long_gather', 'vqa'])
+def test_attention_tcgen05_long_forward_matches_mma_sync(layout, drop, monkeypatch):
+    """Sequences of 257 .. 1024 tokens (VQA at 480 / 384 px): the key-blocked tcgen05 forward with its online softmax
+    (attention_tc_long.cu) against the mma.sync kernel — outputs, log-sum-exp, same dropout mask — with several items per
+    CTA, odd query pairs, short sequences mixed in, masked keys, and the cp.async gather path."""
+    L, ops = _mods()
+    H = 12
+    lay = _long_layout(ops, layout)
+    g = torch.Generator().manual_seed(9)
+    qkv = _rand(lay.tokens, 3 * 64 * H, dtype=torch.bfloat16, seed=31)
+    mask = (torch.rand(lay.tokens, generator=g) > 0.15).to(torch.uint8)
+    valid = torch.zeros(lay.tokens, dtype=torch.bool)
+    for (s0, n0_, s1, n1_) in lay.seq_desc.tolist():
+        mask[s0] = 1
+        valid[s0:s0 + n0_] = True
+        valid[s1:s1 + n1_] = True
+    mask, valid = mask.to(_dev()), valid.to(_dev())
+    seed = torch.tensor([17], dtype=torch.int32, device=_dev())
+    dr = (seed, 3, 0.1) if drop else None
+    res = {}
+    for tc in ('0', '1'):
+        monkeypatch.setenv('MOME_ATTN_TC', tc)
+        res[tc] = ops.attn_fwd(qkv, lay, mask, H, 0.125, dr)
+    (o0, l0), (o1, l1) = res['0'], res['1']
+    assert torch.isfinite(o1[valid].float()).all()
+    assert (o0[valid].float() - o1[valid].float()).abs().max() <= 2.0 ** -6
+    assert rel_err(o1[valid], o0[valid]) < 4e-3
+    desc = lay.seq_desc.long()
+    nlen = (desc[:, 1] + desc[:, 3])[:, None, None]
+    fin = (torch.arange(lay.max_seq_len, device=_dev())[None, None, :] < nlen).expand(lay.num_seqs, H, lay.max_seq_len).reshape(-1)
+    assert (l0[fin] - l1[fin]).abs().max() < 1e-4
+
+
 def test_attention_no_mask_pointer():
     L, ops = _mods()
     seqs, tokens, H = ATTN_CASES[1]
