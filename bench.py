@@ -232,7 +232,7 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------- product arm
-def attention_preflight(batch, device):
+def attention_preflight(batch, device, long_sequences=False):
     """The tcgen05 attention kernels are the default for the step's layouts; before the measurement a child process
     runs them against the mma.sync kernels on this GPU at the step's sizes (tools/attn_bench.py --check: outputs,
     log-sum-exp and gradients, with and without dropout). A child, because a faulting kernel poisons its CUDA context.
@@ -242,8 +242,10 @@ def attention_preflight(batch, device):
     tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'attn_bench.py')
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT')}
     try:
-        r = subprocess.run([sys.executable, tool, '--check', '--tc-bwd', 'p', '--iters', '1', '--batch', str(min(2 * batch, 256)), '--device', str(device)],
-                           env=env, capture_output=True, text=True, timeout=180)
+        cmd = [sys.executable, tool, '--check', '--tc-bwd', 'p', '--iters', '1', '--batch', str(min(2 * batch, 256)), '--device', str(device)]
+        if long_sequences:  # VQA at 480 px: the key-blocked forward and the query-pair backward (40 + 901 / 40 + 577 tokens)
+            cmd += ['--long', str(min(batch, 32))]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=180)
         ok = r.returncode == 0 and 'CHECK OK' in r.stdout
         detail = '' if ok else (r.stdout[-300:] + r.stderr[-300:])
     except Exception as e:  # timeout, missing tool
@@ -371,7 +373,7 @@ def run_mome(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-    attention = attention_preflight(args.batch, local) if args.precision == 'bf16' else {'fwd': 'simt fp32', 'bwd': 'simt fp32'}
+    attention = attention_preflight(args.batch, local, long_sequences=args.workload == 'vqa480') if args.precision == 'bf16' else {'fwd': 'simt fp32', 'bwd': 'simt fp32'}
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
