@@ -308,6 +308,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
       const int s = item / H, h = item - s * H;
       const int n = seq_len(p.seq_desc, s);
       const int tiles = n > kQTile ? 2 : 1;
+      // every group takes every item's `full` phase, also when the item's only tile belongs to the other group: a group that
+      // skipped phases could test a later phase of the same parity before the producer got there (parities alias two fills apart)
+      mbar_wait_park(&full[k & 1], (k >> 1) & 1);
       for (int t = 0; t < tiles; ++t, ++u) {
         if ((u & 1) != g) continue;
         const int stage = k & 1;

@@ -294,11 +294,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_long_kernel(const __g
       cur[1] = cur[0];
       uint32_t nS[2] = {0, 0};        // S MMAs issued per group = phase of s_full / p_full
       uint32_t items_done[2] = {0, 0};  // items finished per group = phase of o_free
-      // a group without a tile in this item (last, odd pair) skips the item
-      auto skip_idle = [&](int g) {
-        while (cur[g].n > 0 && g >= cur[g].nqt) next_item(cur[g]);
-      };
-      skip_idle(1);
       // stage / item bookkeeping: a stage is released when both groups (or the only active one) have issued PV_j,
       // a query buffer when both have issued their last S
       auto release_after = [&](const Cur& c, int g, bool is_pv) {
@@ -322,6 +317,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_long_kernel(const __g
         for (int g = 0; g < 2; ++g) {
           Cur& c = cur[g];
           if (c.n == 0) continue;
+          if (g >= c.nqt) {
+            // group 1 has no tile in this item: its cursor moves on once group 0's cursor has left the item, so that every
+            // barrier phase it tests later has a completed predecessor (phase parities alias two fills apart)
+            if (cur[0].n == 0 || cur[0].k > c.k) next_item(c);
+            continue;
+          }
           const uint32_t stage = (c.kv0 + c.j) % kKVStages, fill = (c.kv0 + c.j) / kKVStages;
           const int nk = min(kKB, pad16(c.n - c.j * kKB));
           const uint32_t slot = tmem_base + g * kSlotCols;
@@ -354,7 +355,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_long_kernel(const __g
             if (++c.j == c.nkv) {
               ++items_done[g];
               next_item(c);
-              skip_idle(g);
             }
           }
         }
@@ -380,7 +380,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_long_kernel(const __g
       const uint32_t kph = (k >> 1) & 1;
       const uint32_t meta = smem_u32(smem + kMetaOff + (k & (kMetaSlots - 1)) * kMetaBytes);
       ++k;
-      if (g >= geo.nqt) continue;  // odd last pair: group 1 has no tile
+      if (g >= geo.nqt) {
+        // Odd last pair (or a one-tile sequence): group 1 has no tile, but it still takes the item's barrier phase. A group
+        // that ran ahead through a stretch of such items (the text sequences of a split layout) would otherwise test a later
+        // phase of the same parity before the producer got there, and read a stale descriptor.
+        wait_bar(&q_full[par], kph);
+        continue;
+      }
       const int s = geo.sh / H, h = geo.sh - s * H;
       const int n = geo.n;
       const int q = (2 * geo.qp + g) * kQTile + row;

@@ -35,12 +35,14 @@ def main():
     bench = {
         'r02_bench_pretrain_base.json': ('r6_bench.log', 'r5_bench.log', 'r4_bench_merged.log'),
         'r02_bench_pretrain_base_nomerge.json': ('r6_bench_nomerge.log', 'r4_bench_nomerge.log',),
+        'r02_bench_reference_arm.json': ('r6_bench_reference.log',),
         'r02_bench_pretrain_base_dedup.json': ('r6_bench_dedup.log', 'r5_bench_dedup.log', 'r3_bench_dedup.log'),
         'r02_bench_vqa480.json': ('r6_bench_vqa480.log', 'r5_bench_vqa480.log', 'r2_bench_vqa480.log'),
         'r02_bench_itc4096.json': ('r6_bench_itc4096.log', 'r5_bench_itc4096.log', 'r2_bench_itc4096.log'),
         'r02_bench_pretrain_large.json': ('r6_bench_large.log', 'r5_bench_large.log', 'r2_bench_large.log'),
-        'r02_bench_n2.json': ('n2_bench.log',), 'r02_bench_n2_zero2.json': ('n2_bench_zero2.log',), 'r02_bench_n2_itc4096.json': ('n2_bench_itc.log',),
-        'r02_bench_n8.json': ('n8_bench.log',),
+        'r02_bench_n2.json': ('n2f_bench.log', 'n2c_ov.log', 'n2_bench.log'), 'r02_bench_n2_zero2.json': ('n2c_noov_zero2.log', 'n2_bench_zero2.log'), 'r02_bench_n2_itc4096.json': ('n2_bench_itc.log',),
+        'r02_bench_n8.json': ('n8f_bench.log', 'n8_bench.log'), 'r02_bench_n8_no_overlap.json': ('n8_bench_noov.log',), 'r02_bench_n8_bf16_reduce.json': ('n8f_bench_bf16.log',),
+        'r02_bench_n8_itc4096.json': ('n8f_bench_itc.log', 'n8_bench_itc.log'),
         'r02_reference_eager_gpu.json': ('r2_ref_eager_pretrain.log',),
     }
     for out, cands in bench.items():
@@ -52,7 +54,8 @@ def main():
                     json.dump(d, f, indent=1)
                 break
     for out, cands in {'r02_gemm_bench.txt': ('r6_gb.log', 'r5_gb.log', 'r4_gb.log'), 'r02_row_bench.txt': ('r6_row.log', 'r4_row.log'),
-                       'r02_row_bench_r01_kernels.txt': ('r3_row_v0.log',), 'r02_attn_bench.txt': ('r6_attn.log', 'r5_attn_bwd3.log', 'r3_attn_bwd1.log'),
+                       'r02_row_bench_r01_kernels.txt': ('r3_row_v0.log',), 'r02_attn_bench.txt': ('r6_attn.log', 'r5_attn_bwd3.log', 'r3_attn_bwd1.log'), 'r02_attn_bench_long.txt': ('r6_attn_long.log', 'r12_attn_long.log'),
+                       'r02_attn_bench_first_tcgen05_backward.txt': ('r6_attn_first_kernel.log', 'r10_attn_1.log'),
                        'r02_gemm_bench_knobs_start_of_round.txt': None}.items():
         if cands is None:
             parts = []
@@ -74,6 +77,18 @@ def main():
             summarize_launches.main(lp, os.path.join(HERE, 'r02_gemm_traffic.json'))
         open(os.path.join(HERE, 'r02_launches_summary.md'), 'w').write(
             f'ncu launch list of ONE eager pretraining step (bench.py --ncu-step; source {os.path.basename(lp)}):\n\n' + buf.getvalue())
+    reps = [os.path.join(G, n) for n in ('r6_attn_bwd_pipe.ncu-rep', 'r6_attn_bwd_pipe_long.ncu-rep', 'r6_attn_fwd_long.ncu-rep', 'r9_attn_fwd.ncu-rep',
+                                          'r9_attn_bwd.ncu-rep')]
+    reps = [r for r in reps if os.path.exists(r)]
+    if reps:
+        import ncu_summary
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            ncu_summary.main(reps)
+        open(os.path.join(HERE, 'r02_attn_ncu_final.md'), 'w').write(
+            'ncu --set full --clock-control none of the attention kernels (tools/attn_bench.py; 256 x [40 | 197] tokens or, for the *_long '
+            'captures, 32 x [40 | 901]; 12 heads; no dropout). Order: pipelined backward, pipelined backward at the VQA layout, key-blocked '
+            'forward at the VQA layout, short forward, first tcgen05 backward (round 1).\n\n' + buf.getvalue())
     for name in ('unit', 'base', 'large', 'vqa480'):
         p = os.path.join(G, f'parity_{name}.json')
         if not os.path.exists(p):

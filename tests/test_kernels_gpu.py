@@ -455,7 +455,9 @@ def test_attention_tcgen05_backward_pipeline_many_items(layout, drop, monkeypatc
 def _long_layout(ops, kind):
     lens = {'long': [(40, 901), (40, 577), (40, 217), (8, 0), (40, 700), (40, 984), (16, 1), (40, 345), (40, 901)],
             'long_gather': [(13, 901), (27, 500), (40, 901), (5, 260)],
-            'vqa': [(40, 901)] * 14}[kind]
+            'vqa': [(40, 901)] * 14,
+            # pre-fusion layers of the VQA step: a long stretch of one-tile text sequences in front of the image sequences
+            'vqa_split': [(40, 0)] * 40 + [(901, 0)] * 6}[kind]
     seqs, t0, t1 = [], 0, sum(a for a, _ in lens)
     for a, b in lens:
         seqs.append((t0, a, t1 if b > 0 else 0, b))
@@ -465,8 +467,46 @@ def _long_layout(ops, kind):
     return ops.PackedLayout(t1, [(0, t1, 'vl')], desc, len(seqs), max(a + b for a, b in lens))
 
 
+def test_attention_long_kernels_stay_inside_their_buffers():
+    """The VQA step's layouts (split: one-tile text sequences, then 901-token image sequences; fused: 941 tokens) with every
+    buffer allocated exactly and surrounded by guard words: nothing outside qkv / out / lse / dqkv / the workspace is written,
+    and the results do not depend on what lies around them."""
+    L, ops = _mods()
+    H = 12
+    for kind in ('vqa_split', 'vqa'):
+        lay = _long_layout(ops, kind)
+        d = 64 * H
+        qkv = _rand(lay.tokens, 3 * d, dtype=torch.bfloat16, seed=41)
+        dout = _rand(lay.tokens, d, dtype=torch.bfloat16, seed=42)
+        mask = torch.ones(lay.tokens, dtype=torch.uint8, device=_dev())
+        guard = 4096
+
+        def guarded(numel, dtype):
+            buf = torch.full((numel + 2 * guard,), 7, dtype=dtype, device=_dev())
+            return buf, buf[guard:guard + numel]
+
+        ob, out = guarded(lay.tokens * d, torch.bfloat16)
+        lb, lse = guarded(lay.num_seqs * H * lay.max_seq_len, torch.float32)
+        gb, dqkv = guarded(lay.tokens * 3 * d, torch.bfloat16)
+        wb, ws = guarded(L.lib().mome_attn_bwd_ws_floats(lay.tokens, lay.num_seqs, lay.max_seq_len, H), torch.float32)
+        L.check(L.lib().mome_attn_fwd(qkv.data_ptr(), L.BF16, lay.seq_desc.data_ptr(), mask.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                                      lay.tokens, lay.num_seqs, lay.max_seq_len, H, 0.125, None, 0, 0.0, L.stream()), 'fwd')
+        L.check(L.lib().mome_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), L.BF16, lay.seq_desc.data_ptr(), mask.data_ptr(),
+                                      lse.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), lay.tokens, lay.num_seqs, lay.max_seq_len, H, 0.125,
+                                      None, 0, 0.0, L.stream()), 'bwd')
+        torch.cuda.synchronize()
+        for name, buf in (('out', ob), ('lse', lb), ('dqkv', gb), ('ws', wb)):
+            assert bool((buf[:guard] == 7).all()) and bool((buf[-guard:] == 7).all()), (kind, name)
+        o_ref, l_ref = ops.attn_fwd(qkv, lay, mask, H, 0.125)
+        assert torch.equal(out.view(lay.tokens, d), o_ref)
+        desc = lay.seq_desc.long()
+        nlen = (desc[:, 1] + desc[:, 3])[:, None, None]
+        fin = (torch.arange(lay.max_seq_len, device=_dev())[None, None, :] < nlen).expand(lay.num_seqs, H, lay.max_seq_len).reshape(-1)
+        assert torch.equal(lse[fin], l_ref[fin])   # slots past a sequence's end are never written
+
+
 @pytest.mark.parametrize('drop', [False, True])
-@pytest.mark.parametrize('layout', ['long', 'long_gather', 'vqa'])
+@pytest.mark.parametrize('layout', ['long', 'long_gather', 'vqa', 'vqa_split'])
 def test_attention_tcgen05_long_forward_matches_mma_sync(layout, drop, monkeypatch):
     """Sequences of 257 .. 1024 tokens (VQA at 480 / 384 px): the key-blocked tcgen05 forward with its online softmax
     (attention_tc_long.cu) against the mma.sync kernel — outputs, log-sum-exp, same dropout mask — with several items per
