@@ -30,9 +30,15 @@ static bool use_tc_long(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC");
   return (e == nullptr || e[0] != '0') && max_seq_len > 256 && max_seq_len <= attn_fwd_tc_long_max_seq_len();
 }
+// shortest layout the tcgen05 kernels take (text-only layouts of <= 64 tokens fill a third of a 128-row tile: the mma.sync
+// kernels measured faster there, tools/attn_bench.py 'text 40'); MOME_ATTN_TC_MIN overrides it for that measurement
+static int tc_min_len() {
+  const char* e = getenv("MOME_ATTN_TC_MIN");
+  return e != nullptr ? atoi(e) : 64;
+}
 static bool use_tc(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC");
-  return (e == nullptr || e[0] != '0') && max_seq_len > 64 && max_seq_len <= 256;
+  return (e == nullptr || e[0] != '0') && max_seq_len > tc_min_len() && max_seq_len <= 256;
 }
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const int32_t* seq_desc, const uint8_t* key_mask, const float* lse,
@@ -51,7 +57,7 @@ int64_t attn_bwd_tc_pipe_extra_ws_floats(int64_t tokens, int max_seq_len, int H)
 // 256 tokens), 0 = mma.sync.
 static bool use_tc_bwd_pipe(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC_BWD");
-  return (e == nullptr || e[0] == '\0' || e[0] == 'p') && max_seq_len > 64 && max_seq_len <= attn_bwd_tc_pipe_max_seq_len();
+  return (e == nullptr || e[0] == '\0' || e[0] == 'p') && max_seq_len > tc_min_len() && max_seq_len <= attn_bwd_tc_pipe_max_seq_len();
 }
 static bool use_tc_bwd(int max_seq_len) {
   const char* e = getenv("MOME_ATTN_TC_BWD");
