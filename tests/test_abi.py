@@ -36,6 +36,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.mome_launch_count() == 0
 
 
+def test_attention_backward_workspace_size():
+    """mome_attn_bwd_ws_floats is host arithmetic (no GPU needed): delta values for every (sequence, head, query), padded to
+    16 bytes, plus — for layouts with sequences longer than 256 tokens only — the fp32 dK / dV accumulators [tokens, 2 d]."""
+    _ensure_built()
+    lib = _lib.lib()
+    H, d = 12, 768
+    assert lib.mome_attn_bwd_ws_floats(128 * 237, 128, 237, H) == 128 * H * 237              # pretraining: no accumulators
+    assert lib.mome_attn_bwd_ws_floats(3 * 200, 3, 200, 5) == (3 * 5 * 200 + 3) // 4 * 4
+    assert lib.mome_attn_bwd_ws_floats(32 * 941, 32, 941, H) == 32 * H * 941 + 32 * 941 * 2 * d   # VQA at 480 px
+    assert lib.mome_attn_bwd_ws_floats(7 * 257, 7, 257, H) == (7 * H * 257 + 3) // 4 * 4 + 7 * 257 * 2 * d
+
+
 def test_struct_layout_matches_header(tmp_path):
     """sizeof of every ABI struct as the C compiler sees include/mome.h == the ctypes mirror in _lib.py."""
     import subprocess
