@@ -41,6 +41,7 @@ def main():
         'r02_bench_itc4096.json': ('r6_bench_itc4096.log', 'r5_bench_itc4096.log', 'r2_bench_itc4096.log'),
         'r02_bench_pretrain_large.json': ('r6_bench_large.log', 'r5_bench_large.log', 'r2_bench_large.log'),
         'r02_bench_n2.json': ('n2f_bench.log', 'n2c_ov.log', 'n2_bench.log'), 'r02_bench_n2_zero2.json': ('n2c_noov_zero2.log', 'n2_bench_zero2.log'), 'r02_bench_n2_itc4096.json': ('n2_bench_itc.log',),
+        'r02_bench_n4.json': ('n4f_bench_n4.log',), 'r02_bench_n4box_n1.json': ('n4f_bench_n1.log',), 'r02_bench_n4box_n2.json': ('n4f_bench_n2.log',),
         'r02_bench_n8.json': ('n8f_bench.log', 'n8_bench.log'), 'r02_bench_n8_no_overlap.json': ('n8_bench_noov.log',), 'r02_bench_n8_bf16_reduce.json': ('n8f_bench_bf16.log',),
         'r02_bench_n8_itc4096.json': ('n8f_bench_itc.log', 'n8_bench_itc.log'),
         'r02_reference_eager_gpu.json': ('r2_ref_eager_pretrain.log',),
