@@ -21,7 +21,7 @@
 //     one is processed, and two 1-tile (text) items are in flight at once;
 //   * a thread fetches the next item's lse / delta while it works on this one.
 //
-// What bounds it now (MOME_ATTN_DBG event trace + tools/umma_probe.cu): with head_dim 64 every MMA has N = 64, i.e. 6 KB of
+// What bounds it now (clock64 event trace of a debugging build, profiles/r02_attn_bwd_ncu.md, + tools/umma_probe.cu): with head_dim 64 every MMA has N = 64, i.e. 6 KB of
 // shared-memory operands for 32 tensor-pipe cycles; operand fetch (~64 B/clk) and the issuing thread (~90 cycles per
 // tcgen05.mma) both sit at ~95 cycles per MMA, 40 MMAs per 128 x 128 block = ~3800 cycles, next to ~3600 cycles of
 // P / dS work per block. Three issuing threads and register-deferred tile stores were tried and measured no faster.
