@@ -8,7 +8,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = [('UTCHMMA', 'tcgen05.mma'), ('UTCBAR', 'tcgen05.commit'), ('LDTM', 'tcgen05.ld'), ('STTM', 'tcgen05.st'), ('UTMALDG', 'TMA tensor load'),
        ('UCGABAR', 'cluster barrier'), ('USETMAXREG', 'setmaxnreg'), ('HMMA', 'mma.sync'), ('LDSM', 'ldmatrix'), ('LDGSTS', 'cp.async'),
-       ('MUFU.EX2', 'ex2.approx'), ('RED', 'red.global.add')]
+       ('MUFU.EX2', 'ex2.approx'), ('REDG', 'red.global.add')]
 
 
 def main():
