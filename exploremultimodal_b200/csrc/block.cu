@@ -27,6 +27,53 @@ inline bool on(const MomeBlockArgs* a, float p) { return a->drop_seed != nullptr
     if (rc_ != MOME_OK) return rc_; \
   } while (0)
 
+// Side stream of the backward: the four weight-gradient GEMMs of a block depend on the dgrad chain but nothing in the block depends on
+// them, so they are forked onto a second (lowest-priority) stream and joined before the call returns. Two persistent GEMMs cannot share
+// an SM (shared memory), but the HBM-bound row kernels of the chain (LayerNorm / LayerScale backward, column sums) can run next to a
+// weight-gradient GEMM: tensor pipe and memory pipe are busy at the same time. Fork / join are event record / wait pairs, which a
+// CUDA-graph capture turns into parallel branches. Opt-in (MOME_BWD_SIDE_STREAM=1): measured on a power-capped B200 the graphed
+// pretraining step gains 0.4 % (122.06 against 122.50 ms; the SM clock drops from 1597 to 1515 MHz as more units are busy at once),
+// the eager step 3 % (122.3 against 126.2 ms).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join = nullptr;
+  bool ok = false;
+};
+SideStream* side_stream() {
+  static const bool enabled = [] { const char* e = getenv("MOME_BWD_SIDE_STREAM"); return e != nullptr && e[0] == '1'; }();
+  if (!enabled || mome::gemm_prof_active()) return nullptr;
+  static SideStream per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (s.stream == nullptr) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = numerically greatest = lowest priority
+    bool ok = cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    s.ok = ok;
+    if (!ok) cudaGetLastError();
+  }
+  return s.ok ? &s : nullptr;
+}
+// everything issued on `main` so far happens before what is issued on the side stream from now on
+inline int fork_to(SideStream* ss, int i, cudaStream_t main) {
+  if (cudaEventRecord(ss->fork[i], main) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork[i], 0) != cudaSuccess) {
+    mome::set_error("block_bwd: fork to the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return MOME_ERR_CUDA;
+  }
+  return MOME_OK;
+}
+inline int join_from(SideStream* ss, cudaStream_t main) {
+  if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(main, ss->join, 0) != cudaSuccess) {
+    mome::set_error("block_bwd: join of the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return MOME_ERR_CUDA;
+  }
+  return MOME_OK;
+}
+
 }  // namespace
 
 extern "C" int mome_block_fwd(const MomeBlockArgs* a, void* stream) {
@@ -114,14 +161,19 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
     dgrad1.group[i].a = at(a->s_dz, s.first_row, hid, es); dgrad1.group[i].b = s.w1; dgrad1.group[i].M = s.rows; dgrad1.group[i].K = hid;
     dgrad1.group[i].out = at(a->s_dh2, s.first_row, d, es);
   }
-  MOME_TRY(mome_gemm(&dgrad2, stream));  // dz = (dbr2 W2) * gelu'(z); per-32-row column sums -> colsum_part
+  SideStream* ss = side_stream();
+  cudaStream_t main_s = static_cast<cudaStream_t>(stream);
+  void* wstream = ss != nullptr ? static_cast<void*>(ss->stream) : stream;  // where the weight-gradient GEMMs go
+  if (ss != nullptr) MOME_TRY(fork_to(ss, 0, main_s));  // dbr2 is there
+  MOME_TRY(mome_gemm(&wgrad2, wstream));  // dW2 += dbr2^T u
+  MOME_TRY(mome_gemm(&dgrad2, stream));   // dz = (dbr2 W2) * gelu'(z); per-32-row column sums -> colsum_part
   for (int i = 0; i < a->num_groups; ++i) {
     const MomeBlockGroup& s = a->group[i];
     MOME_TRY(mome_colreduce(s.colsum_part, (s.rows + 31) / 32, hid, s.db1, stream));
   }
-  MOME_TRY(mome_gemm(&wgrad2, stream));  // dW2 += dbr2^T u
-  MOME_TRY(mome_gemm(&wgrad1, stream));  // dW1 += dz^T h2
-  MOME_TRY(mome_gemm(&dgrad1, stream));  // dh2 = dz W1
+  if (ss != nullptr) MOME_TRY(fork_to(ss, 1, main_s));  // dz is there
+  MOME_TRY(mome_gemm(&wgrad1, wstream));  // dW1 += dz^T h2
+  MOME_TRY(mome_gemm(&dgrad1, stream));   // dh2 = dz W1
   // LN2 backward (+ dx2) fused with the LayerScale backward of the attention branch
   const MomeDropout drop1{on(a, a->p_branch) ? a->drop_seed : nullptr, path ? a->row_scale1 : nullptr, 0, a->drop_salt + 1, a->p_branch};
   MOME_TRY(mome_ln_bwd_scale(a->s_dh2, dt, a->x1, a->mean2, a->rstd2, a->n2w, a->dx2, a->s_dx1, a->dn2w, a->dn2b, a->br1, a->gamma_1,
@@ -130,7 +182,8 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   {
     MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, d, d, d);
     g.group[0].a = a->s_dbr1; g.group[0].b = a->o; g.group[0].M = d; g.group[0].K = T; g.group[0].out = a->dw_proj;
-    MOME_TRY(mome_gemm(&g, stream));
+    if (ss != nullptr) MOME_TRY(fork_to(ss, 2, main_s));  // dbr1 is there
+    MOME_TRY(mome_gemm(&g, wstream));
   }
   {
     MomeGemmArgs g = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, 1, d, d, d, d);
@@ -145,12 +198,16 @@ extern "C" int mome_block_bwd(const MomeBlockArgs* a, void* stream) {
   {
     MomeGemmArgs g = gemm_args(dt, 1, 1, MOME_EPI_ATOMIC, MOME_F32, 1, d, 3 * d, d, d);
     g.group[0].a = a->s_dqkv; g.group[0].b = a->h; g.group[0].M = 3 * d; g.group[0].K = T; g.group[0].out = a->dw_qkv;
-    MOME_TRY(mome_gemm(&g, stream));
+    if (ss != nullptr) MOME_TRY(fork_to(ss, 3, main_s));  // dqkv is there
+    MOME_TRY(mome_gemm(&g, wstream));
   }
   {
     MomeGemmArgs g = gemm_args(dt, 0, 1, MOME_EPI_STORE, dt, 1, d, 3 * d, d, d);
     g.group[0].a = a->s_dqkv; g.group[0].b = a->w_qkv; g.group[0].M = T; g.group[0].K = 3 * d; g.group[0].out = a->s_dh;
     MOME_TRY(mome_gemm(&g, stream));
   }
-  return mome_ln_bwd(a->s_dh, dt, a->x, a->mean1, a->rstd1, a->n1w, a->s_dx1, a->dx, a->dn1w, a->dn1b, T, d, a->ws, a->ws_bytes, stream);
+  MOME_TRY(mome_ln_bwd(a->s_dh, dt, a->x, a->mean1, a->rstd1, a->n1w, a->s_dx1, a->dx, a->dn1w, a->dn1b, T, d, a->ws, a->ws_bytes, stream));
+  // the scratch tensors the weight-gradient GEMMs read are released by the caller when this call returns: join first
+  if (ss != nullptr) MOME_TRY(join_from(ss, main_s));
+  return MOME_OK;
 }

@@ -35,6 +35,8 @@ inline int check_launch(const char* what) {
 int colsum_qv(const void* dqkv, int dtype, int64_t rows, int64_t d, float* dq_bias, float* dv_bias, void* ws, size_t ws_bytes,
               cudaStream_t s);
 
+bool gemm_prof_active();  // gemm_tcgen05.cu: per-launch event profiling (bench.py roofline) is on
+
 int droppath_scales2(const int32_t* row_sample, int64_t rows, const uint32_t* seed, uint32_t salt1, uint32_t salt2, float p, float* out1,
                      float* out2, cudaStream_t stream);
 

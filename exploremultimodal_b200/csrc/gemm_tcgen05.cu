@@ -730,6 +730,15 @@ int gemm_bf16(const MomeGemmArgs* a, cudaStream_t stream) {
 
 }  // namespace mome
 
+namespace mome {
+// block.cu: while per-launch profiling is on, every GEMM stays on the caller's stream (a launch timed next to concurrent kernels
+// would measure the sharing, not the kernel)
+bool gemm_prof_active() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return g_prof_on;
+}
+}  // namespace mome
+
 extern "C" int mome_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(mome::g_prof_mu);
   mome::g_prof_on = on != 0;
